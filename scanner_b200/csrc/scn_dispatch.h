@@ -1,0 +1,57 @@
+// scn_dispatch.h -- host-side dispatch table over the fused-kernel instantiations.
+#pragma once
+#include <cuda_runtime.h>
+#include "scn_kernel.cuh"
+
+namespace scn {
+
+constexpr int kMinLog2N = 8;    // 256
+constexpr int kMaxLog2N = 14;   // 16384
+
+struct KernelVariant {
+  const void* func;       // __global__ entry
+  int threads;
+  size_t smem_bytes;
+  int transforms_per_cta;
+  const char* name;
+};
+
+// One translation unit per sample kind (compiled in parallel); each fills its rows.
+bool variant_byte_complex(int log2n, bool dc, KernelVariant* out);
+bool variant_short(int log2n, bool dc, KernelVariant* out);
+bool variant_short_complex(int log2n, bool dc, KernelVariant* out);
+bool variant_float_complex(int log2n, bool dc, KernelVariant* out);
+
+inline bool find_variant(int kind, int log2n, bool dc, KernelVariant* out) {
+  switch (kind) {
+    case SCN_KIND_BYTE_COMPLEX: return variant_byte_complex(log2n, dc, out);
+    case SCN_KIND_SHORT: return variant_short(log2n, dc, out);
+    case SCN_KIND_SHORT_COMPLEX: return variant_short_complex(log2n, dc, out);
+    case SCN_KIND_FLOAT_COMPLEX: return variant_float_complex(log2n, false, out);
+    default: return false;
+  }
+}
+
+#define SCN_VARIANT_CASE(L, KIND, DC, NAME)                                                   \
+  case L: {                                                                                   \
+    out->func = reinterpret_cast<const void*>(&spectrum_sense_kernel<L, KIND, DC>);          \
+    out->threads = Geometry<L>::THREADS;                                                      \
+    out->smem_bytes = Geometry<L>::kSmemBytes;                                                \
+    out->transforms_per_cta = Geometry<L>::F;                                                 \
+    out->name = NAME "<N=2^" #L ">";                                                          \
+    return true;                                                                              \
+  }
+
+#define SCN_VARIANT_TABLE(KIND, DC, NAME)                                                     \
+  switch (log2n) {                                                                            \
+    SCN_VARIANT_CASE(8, KIND, DC, NAME)                                                       \
+    SCN_VARIANT_CASE(9, KIND, DC, NAME)                                                       \
+    SCN_VARIANT_CASE(10, KIND, DC, NAME)                                                      \
+    SCN_VARIANT_CASE(11, KIND, DC, NAME)                                                      \
+    SCN_VARIANT_CASE(12, KIND, DC, NAME)                                                      \
+    SCN_VARIANT_CASE(13, KIND, DC, NAME)                                                      \
+    SCN_VARIANT_CASE(14, KIND, DC, NAME)                                                      \
+    default: return false;                                                                    \
+  }
+
+}  // namespace scn
