@@ -169,6 +169,20 @@ SCN_API const char* scn_kernel_name(const scn_ctx* ctx);
 SCN_API int scn_kernel_info(const scn_ctx* ctx, int* ctas_per_sm, int* threads, int* smem_bytes,
                             int* regs_per_thread, int* grid);
 
+/* ---- Per-retune-step records (device resident; what ranks exchange over NCCL) -------------
+ * Spectra are numbered globally in step-major order: spectrum u belongs to retune step
+ * u / units_per_step of the FrequencyTable (frequencyTable.cpp:17-36).  This context's batch
+ * holds units [first_unit, first_unit + n_spectra).  d_records receives, for each of n_steps
+ * steps, scn_record_words() uint32: [0] hit total, [1] spectra contributing, [2..] OR of the
+ * hit masks.  Steps this batch does not touch get zeros, so per-rank partial records merge by
+ * sum/OR (scn_merge_step_records) after an all-gather. */
+SCN_API uint32_t scn_record_words(const scn_ctx* ctx);
+SCN_API int scn_summarize_steps(scn_ctx* ctx, const uint32_t* d_hit_mask, const uint32_t* d_hit_count,
+                                uint32_t n_spectra, uint64_t first_unit, uint32_t units_per_step,
+                                uint32_t n_steps, uint32_t* d_records, void* stream);
+SCN_API int scn_merge_step_records(scn_ctx* ctx, const uint32_t* d_parts, uint32_t n_parts,
+                                   uint32_t n_steps, uint32_t* d_out, void* stream);
+
 /* ---- Host-side helpers that restate reference arithmetic --------------------- */
 /* uint32_t(useBandWidth * N / 2.0), process.cpp:85. */
 SCN_API uint32_t scn_use_window(double use_bandwidth, uint32_t sample_count);

@@ -65,6 +65,9 @@ SYMBOLS = [
     ("scn_launch_count", _U64, [_VP]),
     ("scn_kernel_name", C.c_char_p, [_VP]),
     ("scn_kernel_info", _I, [_VP] + [C.POINTER(_I)] * 5),
+    ("scn_record_words", _U32, [_VP]),
+    ("scn_summarize_steps", _I, [_VP, _VP, _VP, _U32, _U64, _U32, _U32, _VP, _VP]),
+    ("scn_merge_step_records", _I, [_VP, _VP, _U32, _U32, _VP, _VP]),
     ("scn_use_window", _U32, [_D, _U32]),
     ("scn_hit_frequency", _U64, [_D, _U32, _U32, _U32]),
     ("scn_frequency_table", _U32, [_U32, _D, _D, _D, _D, C.POINTER(_D), _U32]),
@@ -255,6 +258,21 @@ class SpectrumSense:
         _check(self._lib.scn_launch_device(self._ctx, _VP(d_raw), n_spectra, _VP(d_spectra or None),
                                            _VP(d_masks or None), _VP(d_counts or None),
                                            _VP(d_hits or None), _VP(d_td or None), _VP(stream or None)))
+
+
+    def summarize_steps(self, d_masks: int, d_counts: int, n_spectra: int, first_unit: int,
+                        units_per_step: int, n_steps: int, d_records: int, stream: int = 0) -> None:
+        _check(self._lib.scn_summarize_steps(self._ctx, _VP(d_masks or None), _VP(d_counts or None), n_spectra,
+                                             first_unit, units_per_step, n_steps, _VP(d_records),
+                                             _VP(stream or None)))
+
+    def merge_step_records(self, d_parts: int, n_parts: int, n_steps: int, d_out: int, stream: int = 0) -> None:
+        _check(self._lib.scn_merge_step_records(self._ctx, _VP(d_parts), n_parts, n_steps, _VP(d_out),
+                                                _VP(stream or None)))
+
+    @property
+    def record_words(self) -> int:
+        return self.words + 2
 
 
 def alloc_pinned(nbytes: int) -> tuple[int, np.ndarray]:

@@ -16,6 +16,14 @@
 #include "scn_dispatch.h"
 #include "scn_timedomain.cuh"
 
+namespace scn {
+cudaError_t launch_summarize(const uint32_t* masks, const uint32_t* counts, uint32_t n_spectra,
+                             uint64_t first_unit, uint32_t units_per_step, uint32_t n_steps, uint32_t words,
+                             uint32_t* records, int num_sms, cudaStream_t stream);
+cudaError_t launch_merge(const uint32_t* parts, uint32_t n_parts, uint32_t n_steps, uint32_t rec_words,
+                         uint32_t* out, cudaStream_t stream);
+}  // namespace scn
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -508,6 +516,30 @@ SCN_API int scn_process_host(scn_ctx* c, const void* raw, uint32_t n_spectra, fl
     int rc = collect_front();
     if (rc != SCN_OK) return rc;
   }
+  return SCN_OK;
+}
+
+SCN_API uint32_t scn_record_words(const scn_ctx* c) { return c ? c->words + 2 : 0; }
+
+SCN_API int scn_summarize_steps(scn_ctx* c, const uint32_t* d_hit_mask, const uint32_t* d_hit_count,
+                                uint32_t n_spectra, uint64_t first_unit, uint32_t units_per_step,
+                                uint32_t n_steps, uint32_t* d_records, void* stream) {
+  if (!c || !d_records || units_per_step == 0 || n_steps == 0)
+    return fail(SCN_ERR_INVALID, "summarize_steps: bad arguments");
+  if (n_spectra && (!d_hit_mask || !d_hit_count)) return fail(SCN_ERR_INVALID, "summarize_steps: NULL inputs");
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  SCN_CUDA(scn::launch_summarize(d_hit_mask, d_hit_count, n_spectra, first_unit, units_per_step, n_steps,
+                                 c->words, d_records, c->num_sms, static_cast<cudaStream_t>(stream)));
+  if (n_spectra) c->launches++;
+  return SCN_OK;
+}
+
+SCN_API int scn_merge_step_records(scn_ctx* c, const uint32_t* d_parts, uint32_t n_parts, uint32_t n_steps,
+                                   uint32_t* d_out, void* stream) {
+  if (!c || !d_parts || !d_out || n_parts == 0) return fail(SCN_ERR_INVALID, "merge_step_records: bad arguments");
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  SCN_CUDA(scn::launch_merge(d_parts, n_parts, n_steps, c->words + 2, d_out, static_cast<cudaStream_t>(stream)));
+  c->launches++;
   return SCN_OK;
 }
 

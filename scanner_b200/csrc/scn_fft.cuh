@@ -194,27 +194,35 @@ __device__ __forceinline__ void pass_twiddle(float2 (&v)[kPts], const float2* __
 
 // Scatter of pass P's outputs into the exchange tile (Stockham autosort index):
 // butterfly j = t + m*T, k = j mod Ns, j0 = (j - k)*R + k, output r -> j0 + r*Ns.
+// With the 1-in-16 padding the padded address is LINEAR in r:
+//   Ns == 1 : xpad(16 j + r)     = 17 j + r
+//   Ns >= 16: xpad(j0 + r Ns)    = xpad(j0) + r (Ns + Ns/16)
+// so every store is base + immediate.
 template <int LOG2N, int P>
 __device__ __forceinline__ void pass_scatter(const float2 (&v)[kPts], float2* __restrict__ xch, int t) {
   constexpr int LOG2R = pass_log2r(LOG2N, P);
   constexpr int R = 1 << LOG2R, M = 16 / R, T = (1 << LOG2N) / 16;
   constexpr int LOG2NS = 4 * P;
   constexpr int NS = 1 << LOG2NS;
+  constexpr int RSTRIDE = (NS == 1) ? 1 : (NS + NS / 16);
 #pragma unroll
   for (int m = 0; m < M; m++) {
     const int j = t + m * T;
     const int k = j & (NS - 1);
     const int j0 = ((j - k) << LOG2R) + k;
+    float2* base = xch + xpad(j0);
 #pragma unroll
-    for (int r = 0; r < R; r++) xch[xpad(j0 + r * NS)] = v[m + r * M];
+    for (int r = 0; r < R; r++) base[r * RSTRIDE] = v[m + r * M];
   }
 }
 
+// Gather for the next pass: point t + q*T, i.e. xpad(t) + q*(T + T/16): base + immediate.
 template <int LOG2N>
 __device__ __forceinline__ void pass_gather(float2 (&v)[kPts], const float2* __restrict__ xch, int t) {
   constexpr int T = (1 << LOG2N) / 16;
+  const float2* base = xch + xpad(t);
 #pragma unroll
-  for (int q = 0; q < kPts; q++) v[q] = xch[xpad(t + q * T)];
+  for (int q = 0; q < kPts; q++) v[q] = base[q * (T + T / 16)];
 }
 
 }  // namespace scn

@@ -56,7 +56,13 @@ struct Geometry {
   static constexpr int WORDS = N / 32;                            // mask words per spectrum
   static constexpr int WARPS = THREADS / 32;
   static constexpr int WARPS_PER_FFT = (T >= 32) ? T / 32 : 1;
-  static constexpr size_t kXchBytes = sizeof(float2) * size_t(xch_elems(N)) * F;
+  // Two exchange tiles (ping-pong: one barrier per exchange) whenever they leave room for
+  // several CTAs per SM; the largest size falls back to one tile and two barriers.
+  static constexpr int XBUFS = (LOG2N <= 13) ? 2 : 1;
+  static constexpr size_t kXchTile = sizeof(float2) * size_t(xch_elems(N)) * F;
+  static constexpr size_t kXchBytes = kXchTile * XBUFS;
+  // register budget: 128/thread up to 512-thread CTAs
+  static constexpr int MIN_CTAS = (THREADS <= 128) ? 4 : (THREADS <= 256 ? 2 : 1);
   static constexpr size_t kMaskBytes = sizeof(uint32_t) * size_t(WORDS) * F * 2;   // mask + prefix
   static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * WARPS;
   static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes;
@@ -81,7 +87,7 @@ __device__ __forceinline__ void load_raw_int(const uint8_t* __restrict__ buf, in
 }
 
 template <int LOG2N, int KIND, bool DC>
-__global__ void __launch_bounds__(Geometry<LOG2N>::THREADS)
+__global__ void __launch_bounds__(Geometry<LOG2N>::THREADS, Geometry<LOG2N>::MIN_CTAS)
 spectrum_sense_kernel(const KernelParams p) {
   using G = Geometry<LOG2N>;
   constexpr int N = G::N, T = G::T, F = G::F;
@@ -100,7 +106,8 @@ spectrum_sense_kernel(const KernelParams p) {
   const int t = tid - f * T;         // thread index inside the transform
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  float2* xch = xch_all + size_t(f) * xch_elems(N);
+  float2* xch0 = xch_all + size_t(f) * xch_elems(N);
+  float2* xch1 = (G::XBUFS == 2) ? xch0 + size_t(F) * xch_elems(N) : xch0;
 
   // Window taps for this thread's 16 sample positions stay in registers for the whole launch.
   float w[kPts];
@@ -110,6 +117,19 @@ spectrum_sense_kernel(const KernelParams p) {
   const uint32_t K = p.averaging;
   const uint32_t n_groups = (p.n_spectra + F - 1) / F;
   const uint32_t half = N / 2;
+
+  // Candidate bins of this thread (process.cpp:46-53), fixed for the whole launch:
+  // bit q set <=> FFT bin j = t + q*T is inside the used band and outside the DC hole.
+  uint32_t candbits = 0;
+#pragma unroll
+  for (int q = 0; q < kPts; q++) {
+    const uint32_t j = t + q * T;            // FFT bin (magnitudes[j])
+    const uint32_t i = j ^ half;             // shifted index: (i + N/2) % N == j
+    bool cand = !(j < p.dc_ignore || (N - j) < p.dc_ignore);
+    cand = cand && !(i < (half - p.use_window) || i > (half + p.use_window));
+    candbits |= (cand ? 1u : 0u) << q;
+  }
+  uint32_t xsel = 0;   // ping-pong selector of the exchange tile
 
   for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const uint32_t s = g * F + f;                 // this transform's spectrum
@@ -168,31 +188,35 @@ spectrum_sense_kernel(const KernelParams p) {
       }
 
       // ---- FFT: Stockham passes with shared-memory exchanges ---------------------------
+      // Ping-pong tiles: a tile is rewritten only two exchanges later, and every thread has
+      // passed the intervening barrier after its last read of it, so one barrier per
+      // exchange suffices (two when there is a single tile).
       pass_butterflies<pass_log2r(LOG2N, 0)>(v);
+#define SCN_EXCHANGE(P)                                                      \
+      {                                                                      \
+        float2* xb = (xsel & 1u) ? xch1 : xch0;                              \
+        if constexpr (G::XBUFS == 1) __syncthreads();                        \
+        pass_scatter<LOG2N, P>(v, xb, t);                                    \
+        __syncthreads();                                                     \
+        pass_gather<LOG2N>(v, xb, t);                                        \
+        xsel ^= 1u;                                                          \
+      }
       if constexpr (NP > 1) {
-        __syncthreads();                       // previous readers of xch are done
-        pass_scatter<LOG2N, 0>(v, xch, t);
-        __syncthreads();
-        pass_gather<LOG2N>(v, xch, t);
+        SCN_EXCHANGE(0)
         pass_twiddle<LOG2N, 1>(v, p.twiddles, t);
         pass_butterflies<pass_log2r(LOG2N, 1)>(v);
       }
       if constexpr (NP > 2) {
-        __syncthreads();
-        pass_scatter<LOG2N, 1>(v, xch, t);
-        __syncthreads();
-        pass_gather<LOG2N>(v, xch, t);
+        SCN_EXCHANGE(1)
         pass_twiddle<LOG2N, 2>(v, p.twiddles, t);
         pass_butterflies<pass_log2r(LOG2N, 2)>(v);
       }
       if constexpr (NP > 3) {
-        __syncthreads();
-        pass_scatter<LOG2N, 2>(v, xch, t);
-        __syncthreads();
-        pass_gather<LOG2N>(v, xch, t);
+        SCN_EXCHANGE(2)
         pass_twiddle<LOG2N, 3>(v, p.twiddles, t);
         pass_butterflies<pass_log2r(LOG2N, 3)>(v);
       }
+#undef SCN_EXCHANGE
 
       // ---- power, K-averaging (fp32, buffer order) -------------------------
 #pragma unroll
@@ -209,12 +233,9 @@ spectrum_sense_kernel(const KernelParams p) {
     for (int q = 0; q < kPts; q++) {
       const float pbar = (K == 1) ? acc[q] : __fmul_rn(acc[q], p.inv_averaging);
       db[q] = kDbPerLog2 * __log2f(pbar);
-      const uint32_t j = t + q * T;            // FFT bin (magnitudes[j])
-      const uint32_t i = j ^ half;             // shifted index: (i + N/2) % N == j
-      bool cand = !(j < p.dc_ignore || (N - j) < p.dc_ignore);
-      cand = cand && !(i < (half - p.use_window) || i > (half + p.use_window));
-      if (live && cand && db[q] > p.threshold) hitbits |= 1u << q;
+      hitbits |= (db[q] > p.threshold ? 1u : 0u) << q;     // strict >, NaN never hits (process.cpp:54)
     }
+    hitbits = live ? (hitbits & candbits) : 0u;
     if (p.spectra != nullptr && live) {
       float* out = p.spectra + size_t(s) * N;
 #pragma unroll
