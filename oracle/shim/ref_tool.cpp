@@ -1,0 +1,133 @@
+// ref_tool -- drives the reference's OWN hot-path sources (compiled unmodified from
+// /root/reference with the shim headers in this directory) so the oracle restatement and the GPU
+// path can be checked against what the reference code itself computes.  TEST INFRASTRUCTURE.
+//
+//   ref_tool convert  <kind> <N> <enob> <dc>            stdin: raw buffer(s)   stdout: float32 IQ
+//   ref_tool magnitude <N>                              stdin: complex64[N]    stdout: float32[N]
+//   ref_tool freqtable <fs> <start> <stop> <useBW> <dcIgnore>    stdout: the reference's own table dump
+//   ref_tool scan <kind> <N> <fs> <enob> <dc> <threshold> <win_type> <mode> <buffers_per_sweep>
+//                 <raw_file> <freq_file>
+//        feeds every buffer through SampleQueue::AppendSamples (messageQueue.h:190-237) on a
+//        producer thread and runs ProcessSamples::StartProcessing (process.cpp:316) with ONE worker
+//        (the reference's two workers race on the shared FFT object, fft.cpp:20-25);
+//        stdout is the reference's own output ("Start scan at ...", "freq %lu power_db %f", ...).
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#include <iostream>
+#include <limits>
+#include <cassert>
+#include <cstdint>
+#include <memory>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include "fft.h"
+#include "messageQueue.h"
+#include "signalSource.h"
+#include "process.h"
+
+static std::vector<char> read_all(FILE* f) {
+  std::vector<char> data;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n);
+  return data;
+}
+
+static std::vector<char> read_file(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "ref_tool: cannot open %s\n", path); exit(2); }
+  std::vector<char> d = read_all(f);
+  fclose(f);
+  return d;
+}
+
+static size_t bytes_per_sample(int kind) {
+  switch (kind) {
+    case SampleQueue::ByteComplex: return 2;
+    case SampleQueue::Short: return 4;
+    case SampleQueue::ShortComplex: return 4;
+    case SampleQueue::FloatComplex: return 8;
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: ref_tool <convert|magnitude|freqtable|scan> ...\n"); return 2; }
+  std::string cmd = argv[1];
+  if (cmd == "convert" && argc == 6) {
+    int kind = atoi(argv[2]); uint32_t n = atoi(argv[3]), enob = atoi(argv[4]); bool dc = atoi(argv[5]) != 0;
+    std::vector<char> raw = read_all(stdin);
+    size_t bb = n * bytes_per_sample(kind);
+    std::vector<float> out(2 * size_t(n));
+    for (size_t off = 0; off + bb <= raw.size(); off += bb) {
+      fftwf_complex* dst = reinterpret_cast<fftwf_complex*>(out.data());
+      if (kind == SampleQueue::ByteComplex)
+        Utility::byte_complex_to_float_complex(reinterpret_cast<int8_t(*)[2]>(raw.data() + off), dst, n, enob, dc);
+      else if (kind == SampleQueue::ShortComplex)
+        Utility::short_complex_to_float_complex(reinterpret_cast<int16_t(*)[2]>(raw.data() + off), dst, n, enob, dc);
+      else if (kind == SampleQueue::Short)
+        Utility::short_complex_to_float_complex(reinterpret_cast<int16_t*>(raw.data() + off),
+                                                reinterpret_cast<int16_t*>(raw.data() + off) + n, dst, n, enob, dc);
+      else
+        memcpy(out.data(), raw.data() + off, bb);
+      fwrite(out.data(), sizeof(float), out.size(), stdout);
+    }
+    return 0;
+  }
+  if (cmd == "magnitude" && argc == 3) {
+    uint32_t n = atoi(argv[2]);
+    std::vector<char> raw = read_all(stdin);
+    std::vector<float> out(n);
+    Utility::complex_to_magnitude(reinterpret_cast<fftwf_complex*>(raw.data()), out.data(), n);
+    fwrite(out.data(), sizeof(float), n, stdout);
+    return 0;
+  }
+  if (cmd == "freqtable" && argc == 7) {
+    FrequencyTable table(uint32_t(atof(argv[2])), atof(argv[3]), atof(argv[4]), atof(argv[5]), atof(argv[6]));
+    printf("count %u\n", table.GetFrequencyCount());
+    return 0;
+  }
+  if (cmd == "scan" && argc == 13) {
+    int kind = atoi(argv[2]);
+    uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    bool dc = atoi(argv[6]) != 0;
+    float threshold = float(atof(argv[7]));
+    int win = atoi(argv[8]), mode = atoi(argv[9]);
+    uint32_t per_sweep = atoi(argv[10]);
+    std::vector<char> raw = read_file(argv[11]);
+    std::vector<char> fr = read_file(argv[12]);
+    const double* freqs = reinterpret_cast<const double*>(fr.data());
+    size_t bb = n * bytes_per_sample(kind);
+    size_t nbuf = raw.size() / bb;
+    if (fr.size() / sizeof(double) < nbuf) { fprintf(stderr, "ref_tool: too few frequencies\n"); return 2; }
+    SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
+    ProcessSamples process(n, fs, enob, threshold, gr::fft::window::win_type(win), ProcessSamples::Mode(mode), 1);
+    std::thread producer([&]() {
+      for (size_t b = 0; b < nbuf; b++) {
+        char* p = raw.data() + b * bb;
+        time_t tm = (per_sweep && (b % per_sweep) == 0) ? time_t(1000000000 + b) : 0;
+        if (kind == SampleQueue::ByteComplex)
+          queue.AppendSamples(reinterpret_cast<int8_t(*)[2]>(p), freqs[b], tm);
+        else if (kind == SampleQueue::ShortComplex)
+          queue.AppendSamples(reinterpret_cast<int16_t(*)[2]>(p), freqs[b], tm);
+        else if (kind == SampleQueue::Short)
+          queue.AppendSamples(reinterpret_cast<int16_t*>(p), reinterpret_cast<int16_t*>(p) + n, freqs[b], tm);
+        else
+          queue.AppendSamples(reinterpret_cast<fftwf_complex*>(p), freqs[b], tm);
+      }
+      queue.SetIsDone();
+    });
+    process.StartProcessing(queue);
+    producer.join();
+    fflush(stdout);
+    return 0;
+  }
+  fprintf(stderr, "ref_tool: bad arguments\n");
+  return 2;
+}
