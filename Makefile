@@ -14,7 +14,17 @@ HOSTSRC := $(wildcard $(CSRC)/host/*.cpp)
 HOSTOBJS := $(patsubst $(CSRC)/host/%.cpp,$(BUILD)/host_%.o,$(HOSTSRC))
 KHDRS := $(CSRC)/scn_fft.cuh $(CSRC)/scn_kernel.cuh $(CSRC)/scn_dispatch.h $(CSRC)/scn_timedomain.cuh include/scanner_b200.h
 
-all: $(LIB) oracle
+TOOL      := scanner_b200/scan_b200
+
+SELFTEST  := scanner_b200/host_selftest
+
+all: $(LIB) $(TOOL) $(SELFTEST) oracle
+
+$(SELFTEST): $(CSRC)/tools/host_selftest.cpp $(LIB) $(wildcard $(CSRC)/host/*.h)
+	$(CXX) -O1 -std=c++17 -Iinclude -I$(CSRC)/host -o $@ $< -Lscanner_b200 -lscanner_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
+
+$(TOOL): $(CSRC)/tools/scan_b200.cpp $(LIB) $(wildcard $(CSRC)/host/*.h)
+	$(CXX) -O2 -std=c++17 -Iinclude -I$(CSRC)/host -o $@ $< -Lscanner_b200 -lscanner_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
 $(BUILD):
 	mkdir -p $(BUILD)
@@ -23,7 +33,7 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(KHDRS) | $(BUILD)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(BUILD)/host_%.o: $(CSRC)/host/%.cpp $(wildcard $(CSRC)/host/*.h) include/scanner_b200.h | $(BUILD)
-	$(CXX) -O2 -std=c++17 -fPIC -fvisibility=hidden -Iinclude -I$(CSRC)/host -c $< -o $@
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CSRC)/host -c $< -o $@
 
 $(LIB): $(OBJS) $(HOSTOBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) $(HOSTOBJS) -cudart shared -lpthread
@@ -32,7 +42,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(BUILD) $(LIB)
+	rm -rf $(BUILD) $(LIB) $(TOOL) $(SELFTEST)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -1,0 +1,198 @@
+#include "process.h"
+
+#include <cassert>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace {
+std::mutex g_printMutex;   // whole-buffer output stays contiguous when several workers print
+
+[[noreturn]] void Die(const char* what) {
+  // the reference's error convention in this layer: message to stderr, exit(1)
+  fprintf(stderr, "%s: %s\n", what, scn_last_error());
+  exit(1);
+}
+}  // namespace
+
+ProcessSamples::ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_t enob, float threshold,
+                               int windowType, Mode mode, uint32_t threadCount, std::string fileNameBase,
+                               double useBandWidth, double dcIgnoreWidth, uint32_t preTrigger,
+                               uint32_t postTrigger)
+    : m_sampleCount(numSamples), m_sampleRate(sampleRate), m_enob(enob), m_threshold(threshold),
+      m_windowType(windowType), m_mode(mode), m_threadCount(threadCount), m_fileNameBase(fileNameBase),
+      m_useWindow(scn_use_window(useBandWidth, numSamples)),   // process.cpp:85
+      m_dcIgnoreWindow(4),                                     // process.cpp:87: hard-coded, dcIgnoreWidth unused
+      m_preTrigger(preTrigger), m_postTrigger(postTrigger), m_window(numSamples) {
+  (void)dcIgnoreWidth;
+  assert(mode > Illegal && mode <= FrequencyDomain);
+  assert(threadCount >= 1 && threadCount <= MAX_THREADS);
+  if (scn_window_build(windowType, numSamples, m_window.data()) != SCN_OK) Die("FFTWindow");
+}
+
+ProcessSamples::~ProcessSamples() {}
+
+scn_ctx* ProcessSamples::CreateContext(SampleQueue::SampleKind kind, uint32_t enob, bool correctDC,
+                                       uint32_t maxSpectra) {
+  scn_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.device = m_device;
+  cfg.sample_count = m_sampleCount;
+  cfg.sample_rate = m_sampleRate;
+  cfg.enob = enob;
+  cfg.sample_kind = uint32_t(kind);               // same numbering (messageQueue.h:31-37)
+  cfg.correct_dc_offset = correctDC ? 1 : 0;
+  cfg.averaging = (m_mode == FrequencyDomain) ? m_averaging : 1;
+  cfg.mode = (m_mode == TimeDomain) ? SCN_MODE_TIME_DOMAIN : SCN_MODE_FREQUENCY_DOMAIN;
+  cfg.threshold = m_threshold;
+  cfg.use_window = m_useWindow;
+  cfg.dc_ignore_window = m_dcIgnoreWindow;
+  cfg.window = m_window.data();
+  cfg.max_spectra = maxSpectra;
+  cfg.max_hits_per_spectrum = 0;                  // == N: every hit is reported, like the reference
+  cfg.flags = SCN_OUT_HITS;
+  cfg.ticket_slots = 2;
+  scn_ctx* ctx = nullptr;
+  if (scn_create(&cfg, &ctx) != SCN_OK) Die("scn_create");
+  return ctx;
+}
+
+void ProcessSamples::TimeToString(time_t t, char* buffer, uint32_t length) {
+  struct tm tmv;
+  if (localtime_r(&t, &tmv) == nullptr) { perror("localtime"); exit(1); }
+  if (strftime(buffer, length, "%Y%m%d-%T", &tmv) == 0) { fprintf(stderr, "strftime returned 0"); exit(1); }
+}
+
+void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t sequenceId) {
+  // Trigger/record bookkeeping of process.cpp:250-270.  The recording itself (file I/O) is out of
+  // scope; the window of sequence ids that WOULD be recorded is still tracked and forwarded.
+  if (m_writing) {
+    if (doWrite) {
+      uint64_t end = sequenceId + m_postTrigger + 1, cur = m_endSequenceId;
+      while (cur < end && !m_endSequenceId.compare_exchange_weak(cur, end)) {}
+    } else if (sequenceId == m_endSequenceId) {
+      m_sampleQueue->EndWrite(sequenceId);
+      m_writing = false;
+    }
+  } else if (doWrite && !m_fileNameBase.empty()) {
+    char name[320], tbuf[64];
+    TimeToString(time(nullptr), tbuf, sizeof(tbuf));
+    snprintf(name, sizeof(name), "%s%s-%.0f", m_fileNameBase.c_str(), tbuf, centerFrequency);
+    const uint64_t dec = sequenceId < m_preTrigger ? sequenceId : m_preTrigger;
+    m_sampleQueue->BeginWrite(sequenceId - dec, name);
+    m_writing = true;
+    m_endSequenceId = sequenceId + m_postTrigger + 1;
+  }
+}
+
+void ProcessSamples::ThreadWorker(uint32_t threadId) {
+  (void)threadId;
+  SampleQueue* q = m_sampleQueue;
+  const uint32_t K = (m_mode == FrequencyDomain) ? m_averaging : 1;
+  const uint32_t maxSpectra = (m_maxBatch + K - 1) / K;
+  scn_ctx* ctx = CreateContext(q->m_kind, q->GetEnob(), q->GetCorrectDCOffset(), maxSpectra);
+  const size_t bufBytes = q->GetBufferBytes();
+  const uint32_t N = m_sampleCount;
+  void* staging = nullptr;                              // contiguous pinned batch
+  if (scn_alloc_pinned(bufBytes * size_t(maxSpectra) * K, &staging) != SCN_OK) Die("scn_alloc_pinned");
+  std::vector<uint32_t> counts(maxSpectra);
+  std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * N : 0);
+  std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
+  std::vector<SampleQueue::MessageType*> batch;
+
+  while (uint32_t n = q->GetNextBatch(batch, maxSpectra * K, K)) {
+    uint32_t nSpectra = n / K;
+    if (nSpectra == 0) {                                // trailing partial group at end of stream: dropped
+      for (auto* m : batch) q->MessageProcessed(m);
+      continue;
+    }
+    for (uint32_t i = 0; i < nSpectra * K; i++)
+      memcpy(static_cast<char*>(staging) + size_t(i) * bufBytes, batch[i]->GetData(), bufBytes);
+    uint32_t ticket = 0;
+    if (scn_submit(ctx, staging, nSpectra, &ticket) != SCN_OK) Die("scn_submit");
+    if (scn_collect(ctx, ticket, nullptr, nullptr, counts.data(), hits.empty() ? nullptr : hits.data(),
+                    tdmm.empty() ? nullptr : tdmm.data()) != SCN_OK)
+      Die("scn_collect");
+    m_launches++;
+
+    std::lock_guard<std::mutex> lock(g_printMutex);
+    for (uint32_t s = 0; s < nSpectra; s++) {
+      // the first message of the group carries the spectrum's identity
+      SampleQueue::MessageHeader& header = batch[size_t(s) * K]->GetHeader();
+      for (uint32_t k = 0; k < K; k++) {
+        SampleQueue::MessageHeader& h = batch[size_t(s) * K + k]->GetHeader();
+        if (h.m_time != 0 && m_out) {                   // process.cpp:280-287
+          char tbuf[64];
+          TimeToString(h.m_time, tbuf, sizeof(tbuf));
+          fprintf(m_out, "Start scan at %s\n", tbuf);
+          fflush(m_out);
+        }
+      }
+      bool doWrite = false;
+      if (m_mode == TimeDomain) {
+        doWrite = counts[s] != 0;                       // process.cpp:226-235
+        if (doWrite && m_out) {
+          fprintf(m_out, "Sequence[%llu]: ", (unsigned long long)header.m_sequenceId);
+          fprintf(m_out, "Max signal %f above threshold %f frequency %.0f, min %f\n", tdmm[2 * s],
+                  m_threshold, header.m_frequency, tdmm[2 * s + 1]);
+        }
+      } else {
+        const uint32_t c = counts[s];
+        for (uint32_t r = 0; r < c && r < N; r++) {
+          const scn_hit& h = hits[size_t(s) * N + r];
+          const uint64_t hz = scn_hit_frequency(header.m_frequency, m_sampleRate, N, h.bin);
+          if (m_out) fprintf(m_out, "freq %lu power_db %f\n", (unsigned long)hz, h.power_db);   // process.cpp:57
+          if (m_sink) m_sink(Detection{header.m_sequenceId, header.m_frequency, hz, h.power_db, h.bin});
+        }
+        m_hitCount += c;
+        doWrite = c > 1047;                             // process.cpp:62
+      }
+      if (doWrite) {
+        if (m_out) fflush(m_out);
+      } else {
+        q->SendAck();                                   // process.cpp:303-307
+      }
+      ProcessWrite(doWrite, header.m_frequency, header.m_sequenceId);
+    }
+    for (auto* m : batch) q->MessageProcessed(m);       // process.cpp:309
+    m_buffersProcessed += n;
+  }
+  scn_free_pinned(staging);
+  scn_destroy(ctx);
+}
+
+bool ProcessSamples::StartProcessing(SampleQueue& sampleQueue) {
+  m_sampleQueue = &sampleQueue;
+  for (uint32_t t = 0; t < m_threadCount; t++) {
+    if (m_out) fprintf(m_out, "Starting process thread %u\n", t);
+    m_threads[t] = new std::thread(&ProcessSamples::ThreadWorker, this, t);
+  }
+  for (uint32_t t = 0; t < m_threadCount; t++) {
+    m_threads[t]->join();
+    delete m_threads[t];
+    m_threads[t] = nullptr;
+    if (m_out) fprintf(m_out, "Stopped process thread %u\n", t);
+  }
+  return true;
+}
+
+void ProcessSamples::Run(int16_t sample_buffer[][2], uint32_t centerFrequency) {
+  // Synchronous single-buffer path (process.cpp:131-144): convert -> window -> FFT -> detect on raw
+  // int16 IQ.  (The reference's version dereferences a null header in process_fft and crashes;
+  // here the centre frequency argument is used.)
+  scn_ctx* ctx = CreateContext(SampleQueue::ShortComplex, m_enob, false, 1);
+  std::vector<uint32_t> count(1);
+  std::vector<scn_hit> hits(m_sampleCount);
+  if (m_mode == FrequencyDomain) {
+    if (scn_process_host(ctx, sample_buffer, 1, nullptr, nullptr, count.data(), hits.data(), nullptr) != SCN_OK)
+      Die("scn_process_host");
+    for (uint32_t r = 0; r < count[0]; r++) {
+      const uint64_t hz = scn_hit_frequency(double(centerFrequency), m_sampleRate, m_sampleCount, hits[r].bin);
+      if (m_out) fprintf(m_out, "freq %lu power_db %f\n", (unsigned long)hz, hits[r].power_db);
+      if (m_sink) m_sink(Detection{0, double(centerFrequency), hz, hits[r].power_db, hits[r].bin});
+    }
+    m_hitCount += count[0];
+  }
+  m_launches++;
+  scn_destroy(ctx);
+}

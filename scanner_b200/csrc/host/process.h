@@ -1,0 +1,84 @@
+// ProcessSamples -- the consumer side of the plugin surface.  Same constructor arguments, Mode enum
+// and entry points as the reference's ProcessSamples (process.h:23-91): StartProcessing(SampleQueue&)
+// spawns `threadCount` worker threads and joins them; Run() is the synchronous single-buffer call.
+//
+// Each worker owns one scn_ctx (the C ABI is thread-compatible) and replaces the reference's
+// per-message body (process.cpp:292-299: memcpy -> window -> FFT -> process_fft) with: drain up to
+// `maxBatch` raw messages from the queue, ONE fused GPU launch for the whole batch
+// (scn_submit/scn_collect), then, per message in sequence order, the reference's own bookkeeping
+// (process.cpp:280-287 "Start scan at", :57 "freq %lu power_db %f", :303-309 ack / ProcessWrite /
+// MessageProcessed).  With threadCount == 1 the output is line for line what the reference prints.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sampleQueue.h"
+#include "scanner_b200.h"
+
+class SignalSource;
+
+class ProcessSamples {
+ public:
+  enum Mode { Illegal, TimeDomain, FrequencyDomain };
+
+  // One detection handed to the optional sink, in print order.
+  struct Detection {
+    uint64_t sequenceId;
+    double centerFrequency;
+    uint64_t frequencyHz;     // process.cpp:55-57
+    float powerDb;
+    uint32_t bin;
+  };
+
+  ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_t enob, float threshold,
+                 int windowType /* SCN_WIN_*, == gr::fft::window::win_type */, Mode mode,
+                 uint32_t threadCount = 1, std::string fileNameBase = "", double useBandWidth = 0.75,
+                 double dcIgnoreWidth = 0.0, uint32_t preTrigger = 2, uint32_t postTrigger = 4);
+  ~ProcessSamples();
+
+  void Run(int16_t sample_buffer[][2], uint32_t centerFrequency);
+  bool StartProcessing(SampleQueue& sampleQueue);
+
+  // GPU-path options (defaults reproduce the reference's behaviour)
+  void SetDevice(int device) { m_device = device; }
+  void SetAveraging(uint32_t k) { m_averaging = k ? k : 1; }
+  void SetMaxBatch(uint32_t maxBatch) { m_maxBatch = maxBatch ? maxBatch : 1; }
+  void SetOutput(FILE* out) { m_out = out; }                               // nullptr silences printing
+  void SetDetectionSink(std::function<void(const Detection&)> sink) { m_sink = std::move(sink); }
+  uint64_t GetBuffersProcessed() const { return m_buffersProcessed; }
+  uint64_t GetHitCount() const { return m_hitCount; }
+  uint64_t GetLaunchCount() const { return m_launches; }
+  bool m_writeData = false;
+
+ private:
+  static const uint32_t MAX_THREADS = 8;
+  void ThreadWorker(uint32_t threadId);
+  scn_ctx* CreateContext(SampleQueue::SampleKind kind, uint32_t enob, bool correctDC, uint32_t maxSpectra);
+  void TimeToString(time_t t, char* buffer, uint32_t length);
+  void ProcessWrite(bool doWrite, double centerFrequency, uint64_t sequenceId);
+
+  uint32_t m_sampleCount, m_sampleRate, m_enob;
+  float m_threshold;
+  int m_windowType;
+  Mode m_mode;
+  uint32_t m_threadCount;
+  std::string m_fileNameBase;
+  uint32_t m_useWindow, m_dcIgnoreWindow;
+  uint32_t m_preTrigger, m_postTrigger;
+  SampleQueue* m_sampleQueue = nullptr;
+  std::thread* m_threads[MAX_THREADS] = {};
+  std::vector<float> m_window;
+  int m_device = 0;
+  uint32_t m_averaging = 1;
+  uint32_t m_maxBatch = 1024;
+  FILE* m_out = stdout;
+  std::function<void(const Detection&)> m_sink;
+  std::atomic<uint64_t> m_buffersProcessed{0}, m_hitCount{0}, m_launches{0};
+  std::atomic<bool> m_writing{false};
+  std::atomic<uint64_t> m_endSequenceId{0};
+};

@@ -1,0 +1,179 @@
+#include "sampleQueue.h"
+
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "scanner_b200.h"
+
+static size_t BytesPerSample(SampleQueue::SampleKind kind) {
+  switch (kind) {
+    case SampleQueue::ByteComplex: return 2;
+    case SampleQueue::Short: return 4;
+    case SampleQueue::ShortComplex: return 4;
+    case SampleQueue::FloatComplex: return 8;
+    default: return 0;
+  }
+}
+
+SampleQueue::SampleQueue(SampleKind kind, uint32_t enob, uint32_t sampleCount, uint32_t bufferCount,
+                         bool correctDCOffset, bool doWrite)
+    : m_kind(kind), m_enob(enob), m_sampleCount(sampleCount), m_bufferCount(bufferCount),
+      m_correctDCOffset(correctDCOffset), m_doWrite(doWrite),
+      m_bufferBytes(size_t(sampleCount) * BytesPerSample(kind)) {
+  assert(kind > Illegal && kind <= FloatComplex);
+  // like the reference's pool: 10 % more messages than queue slots (messageQueue.h:150)
+  const uint32_t poolCount = uint32_t(bufferCount * 1.1) + 1;
+  if (scn_alloc_pinned(m_bufferBytes * poolCount, &m_slab) != SCN_OK) {
+    // no CUDA runtime / device: the queue itself still works from pageable memory; the GPU consumer
+    // will fail loudly when it is created.
+    m_slab = nullptr;
+  }
+  m_messages.resize(poolCount);
+  for (uint32_t i = 0; i < poolCount; i++) {
+    MessageType& m = m_messages[i];
+    m.m_bytes = m_bufferBytes;
+    m.m_data = m_slab ? static_cast<char*>(m_slab) + size_t(i) * m_bufferBytes : malloc(m_bufferBytes);
+    m.m_header = MessageHeader{MessageHeader::Free, 0, 0.0, 0, 0};
+    m_free.push_back(&m);
+  }
+}
+
+SampleQueue::~SampleQueue() {
+  if (m_slab) {
+    scn_free_pinned(m_slab);
+  } else {
+    for (auto& m : m_messages) free(m.m_data);
+  }
+}
+
+SampleQueue::MessageType* SampleQueue::Allocate() {
+  std::unique_lock<std::mutex> lock(m_poolMutex);
+  m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
+  MessageType* m = m_free.back();
+  m_free.pop_back();
+  return m;
+}
+
+void SampleQueue::Free(MessageType* m) {
+  std::unique_lock<std::mutex> lock(m_poolMutex);
+  m->m_header.m_kind = MessageHeader::Free;
+  m_free.push_back(m);
+  m_poolAvailable.notify_one();
+}
+
+void SampleQueue::SynchronizedAppend(const void* a, size_t aBytes, const void* b, size_t bBytes,
+                                     double centerFrequency, time_t time) {
+  if (time) m_iterationCount++;
+  if (m_dropFirstSweep && m_iterationCount < 2) {      // messageQueue.h:67-72
+    m_dropped++;
+    return;
+  }
+  MessageType* message = Allocate();
+  memcpy(message->m_data, a, aBytes);
+  if (bBytes) memcpy(static_cast<char*>(message->m_data) + aBytes, b, bBytes);
+  MessageHeader& header = message->m_header;
+  header.m_time = time;
+  header.m_frequency = centerFrequency;
+  header.m_kind = MessageHeader::ProcessData;
+  header.m_referenceCount = 0;
+  std::unique_lock<std::mutex> lock(m_mutex);
+  header.m_sequenceId = m_nextBufferSequenceId++;
+  m_conditionFull.wait(lock, [this] { return m_buffer.size() < m_bufferCount; });
+  const bool wake = m_buffer.empty();
+  m_buffer.push_back(message);
+  if (wake) m_conditionEmpty.notify_all();
+  ClearAck();
+}
+
+void SampleQueue::AppendSamples(int16_t* realSamples, int16_t* imagSamples, double centerFrequency, time_t time) {
+  assert(m_kind == Short);
+  const size_t half = size_t(m_sampleCount) * sizeof(int16_t);
+  SynchronizedAppend(realSamples, half, imagSamples, half, centerFrequency, time);   // re block, then im block
+}
+
+void SampleQueue::AppendSamples(int16_t shortComplexSamples[][2], double centerFrequency, time_t time) {
+  assert(m_kind == ShortComplex);
+  SynchronizedAppend(shortComplexSamples, m_bufferBytes, nullptr, 0, centerFrequency, time);
+}
+
+void SampleQueue::AppendSamples(int8_t (*byteComplexSamples)[2], double centerFrequency, time_t time) {
+  assert(m_kind == ByteComplex);
+  SynchronizedAppend(byteComplexSamples, m_bufferBytes, nullptr, 0, centerFrequency, time);
+}
+
+void SampleQueue::AppendSamples(fftwf_complex* floatComplexSamples, double centerFrequency, time_t time) {
+  assert(m_kind == FloatComplex);
+  SynchronizedAppend(floatComplexSamples, m_bufferBytes, nullptr, 0, centerFrequency, time);
+}
+
+SampleQueue::MessageType* SampleQueue::GetNextSamples() {
+  std::unique_lock<std::mutex> lock(m_mutex);
+  m_conditionEmpty.wait(lock, [this] { return m_done || !m_buffer.empty(); });
+  if (m_buffer.empty()) return nullptr;
+  const bool wake = m_buffer.size() >= m_bufferCount;
+  MessageType* message = m_buffer.front();
+  m_buffer.pop_front();
+  if (wake) m_conditionFull.notify_one();
+  return message;
+}
+
+uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple) {
+  out.clear();
+  if (multiple == 0) multiple = 1;
+  std::unique_lock<std::mutex> lock(m_mutex);
+  // a group of `multiple` buffers forms one averaged spectrum: wait for a whole group (or the end)
+  m_conditionEmpty.wait(lock, [&] { return m_done || m_buffer.size() >= multiple; });
+  size_t take = m_buffer.size() < maxCount ? m_buffer.size() : maxCount;
+  if (!(m_done && m_buffer.size() <= maxCount)) take -= take % multiple;
+  if (take == 0) return 0;
+  const bool wake = m_buffer.size() >= m_bufferCount;
+  for (size_t i = 0; i < take; i++) {
+    out.push_back(m_buffer.front());
+    m_buffer.pop_front();
+  }
+  if (wake) m_conditionFull.notify_all();
+  return uint32_t(take);
+}
+
+void SampleQueue::MessageProcessed(MessageType* message) {
+  assert(message->m_header.m_kind != MessageHeader::Illegal);
+  // The reference parks processed messages in a write-history ring for triggered recording
+  // (messageQueue.h:259-273); recording is out of scope here, so the message returns to the pool.
+  Free(message);
+}
+
+void SampleQueue::BeginWrite(uint64_t startSequenceId, std::string fileName) {
+  printf("BeginWrite %s: %lu\n", fileName.c_str(), (unsigned long)startSequenceId);
+  m_writeStartSequenceId = startSequenceId;
+  m_writeEndSequenceId = UINT64_MAX;
+}
+
+void SampleQueue::EndWrite(uint64_t sequenceId) {
+  printf("EndWrite %lu\n", (unsigned long)sequenceId);
+  m_writeEndSequenceId = sequenceId;
+}
+
+void SampleQueue::SetIsDone() {
+  std::unique_lock<std::mutex> lock(m_mutex);
+  m_done = true;
+  m_conditionEmpty.notify_all();
+}
+
+bool SampleQueue::GetIsDone() {
+  std::unique_lock<std::mutex> lock(m_mutex);
+  return m_done;
+}
+
+bool SampleQueue::ReceivedAck() { return m_acknowledged; }
+
+void SampleQueue::SendAck() {
+  bool expected = false;
+  m_acknowledged.compare_exchange_strong(expected, true);
+}
+
+void SampleQueue::ClearAck() {
+  bool expected = true;
+  m_acknowledged.compare_exchange_strong(expected, false);
+}

@@ -1,0 +1,117 @@
+// SampleQueue -- the live hand-off between a SignalSource (producer thread) and ProcessSamples
+// (consumer threads).  Same public surface as the reference's SampleQueue = MessageQueue<fftwf_complex>
+// (messageQueue.h:11-328): the four AppendSamples overloads, GetNextSamples / MessageProcessed,
+// SetIsDone / GetIsDone, SendAck / ReceivedAck / ClearAck, MessageHeader and SampleKind.
+//
+// What is different, by design: AppendSamples stores the RAW device samples (2/4/8 bytes per
+// sample) in pinned host memory and does NOT convert them -- the reference converts to fp32 on the
+// producer thread (messageQueue.h:196,210,223); here conversion is fused into the GPU kernel, so
+// a message is 4x (int8) / 2x (int16) smaller and is DMA-able as it lies.  Semantics kept:
+//   * caller keeps ownership of its buffer, the queue copies (messageQueue.h:74-75);
+//   * everything before the SECOND scan-start marker (time != 0) is dropped (messageQueue.h:67-72)
+//     unless SetDropFirstSweep(false);
+//   * sequence ids count accepted buffers; FIFO delivery; bounded: Append blocks when full.
+// GetNextBatch() is the batched form of GetNextSamples() the GPU consumer uses.
+// The triggered-recording writer thread (messageQueue.h:98-139) is out of scope (disk I/O):
+// BeginWrite/EndWrite only keep the requested window.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <ctime>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+typedef float fftwf_complex[2];   // the only thing the plugin surface used from <fftw3.h>
+
+class SampleQueue {
+ public:
+  struct MessageHeader {
+    enum MessageKind { Illegal = 0, ProcessData, WriteData, WriteDataAndStop, Free } m_kind;
+    uint32_t m_referenceCount;
+    double m_frequency;
+    uint64_t m_sequenceId;
+    time_t m_time;
+  };
+  enum SampleKind { Illegal = 0, ByteComplex, Short, ShortComplex, FloatComplex };
+
+  // One pooled message: header + raw bytes (pinned).
+  class MessageType {
+   public:
+    MessageHeader m_header;
+    MessageHeader& GetHeader() { return m_header; }
+    void* GetData() { return m_data; }           // raw samples of the queue's SampleKind
+    size_t GetDataBytes() const { return m_bytes; }
+   private:
+    friend class SampleQueue;
+    void* m_data = nullptr;
+    size_t m_bytes = 0;
+  };
+
+  SampleKind m_kind;
+
+  SampleQueue(SampleKind kind, uint32_t enob, uint32_t sampleCount, uint32_t bufferCount,
+              bool correctDCOffset, bool doWrite);
+  ~SampleQueue();
+  SampleQueue(const SampleQueue&) = delete;
+  SampleQueue& operator=(const SampleQueue&) = delete;
+
+  void AppendSamples(int16_t* realSamples, int16_t* imagSamples, double centerFrequency, time_t time);
+  void AppendSamples(int16_t shortComplexSamples[][2], double centerFrequency, time_t time);
+  void AppendSamples(int8_t (*byteComplexSamples)[2], double centerFrequency, time_t time);
+  void AppendSamples(fftwf_complex* floatComplexSamples, double centerFrequency, time_t time);
+
+  MessageType* GetNextSamples();                                   // nullptr == done and drained
+  // Blocks for the first message, then takes what is queued: up to maxCount, a multiple of `multiple`
+  // unless the queue is done.  Returns the number taken (0 == done and drained).
+  uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1);
+  void MessageProcessed(MessageType* message);
+
+  void BeginWrite(uint64_t startSequenceId, std::string fileName);
+  void EndWrite(uint64_t sequenceId);
+  void SetIsDone();
+  bool GetIsDone();
+  bool ReceivedAck();
+  void SendAck();
+  void ClearAck();
+
+  void SetDropFirstSweep(bool drop) { m_dropFirstSweep = drop; }
+  uint32_t GetEnob() const { return m_enob; }
+  uint32_t GetSampleCount() const { return m_sampleCount; }
+  bool GetCorrectDCOffset() const { return m_correctDCOffset; }
+  size_t GetBufferBytes() const { return m_bufferBytes; }
+  uint64_t GetAcceptedCount() const { return m_nextBufferSequenceId; }
+  uint64_t GetDroppedCount() const { return m_dropped; }
+
+ private:
+  void SynchronizedAppend(const void* a, size_t aBytes, const void* b, size_t bBytes,
+                          double centerFrequency, time_t time);
+  MessageType* Allocate();
+  void Free(MessageType* m);
+
+  uint32_t m_enob;
+  uint32_t m_sampleCount;
+  uint32_t m_bufferCount;
+  bool m_correctDCOffset;
+  bool m_doWrite;
+  bool m_dropFirstSweep = true;
+  size_t m_bufferBytes;
+  uint32_t m_iterationCount = 0;
+  uint64_t m_nextBufferSequenceId = 0;
+  uint64_t m_dropped = 0;
+  bool m_done = false;
+  std::atomic<bool> m_acknowledged{true};
+  uint64_t m_writeStartSequenceId = 0, m_writeEndSequenceId = 0;
+
+  std::mutex m_mutex;
+  std::condition_variable m_conditionEmpty, m_conditionFull;
+  std::deque<MessageType*> m_buffer;          // FIFO of filled messages
+  // pool
+  std::mutex m_poolMutex;
+  std::condition_variable m_poolAvailable;
+  std::vector<MessageType> m_messages;
+  std::vector<MessageType*> m_free;
+  void* m_slab = nullptr;                     // one pinned allocation backing every message
+};

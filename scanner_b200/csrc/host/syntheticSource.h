@@ -1,0 +1,61 @@
+// SyntheticSource / ReplaySource -- SignalSource plugins that stand in for SDR hardware.
+//
+// SyntheticSource generates seeded IQ per (retune step, buffer): complex white Gaussian noise
+// (sigma = 0.05 FS per rail) + up to 4 complex tones at random shifted-bin centres inside the used
+// band, amplitudes log-uniform in [-40, -3] dBFS, +0.01 FS DC, quantised round-to-nearest with
+// saturation.  Counter-based generator (splitmix64 of seed/step/buffer/sample),
+// so any buffer can be regenerated independently -- which is what lets ranks own disjoint retune steps.
+// Its ThreadWorker follows the pattern of the reference's sync sources (bladerfSource.cpp:256-300):
+// while (!GetIsDone()) { f = GetCurrentFrequency(); fill; GetNextFrequency(); AppendSamples(..., isScanStart ? time : 0); }
+//
+// ReplaySource feeds recorded raw buffers + their centre frequencies from memory (tests, captures).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "signalSource.h"
+
+class SyntheticSource : public SignalSource {
+ public:
+  SyntheticSource(SampleQueue::SampleKind kind, uint32_t enob, uint64_t seed, uint32_t buffersPerStep,
+                  uint32_t sampleRate, uint32_t sampleCount, double startFrequency, double stopFrequency,
+                  double useBandWidth = 0.75, double dcIgnoreWidth = 0.0);
+  bool GetNextSamples(SampleQueue* sampleQueue, double_t& centerFrequency) override;
+  bool StartStreaming(uint32_t numIterations, SampleQueue& sampleQueue) override;
+  void ThreadWorker() override;
+  double Retune(double frequency) override;
+
+  // Fills `raw` (one buffer of the source's kind) for (sweep, step, buffer); deterministic.
+  void Generate(uint32_t sweep, uint32_t step, uint32_t buffer, void* raw) const;
+  static size_t BufferBytes(SampleQueue::SampleKind kind, uint32_t sampleCount);
+
+ private:
+  SampleQueue::SampleKind m_kind;
+  uint32_t m_enob;
+  uint64_t m_seed;
+  uint32_t m_buffersPerStep;
+  double m_useBandWidth;
+  double m_currentFrequency = 0.0;
+};
+
+class ReplaySource : public SignalSource {
+ public:
+  // raw: nBuffers contiguous buffers; frequencies: nBuffers centre frequencies; buffersPerSweep marks
+  // scan starts (time != 0 on the first buffer of each sweep), 0 == never.
+  ReplaySource(SampleQueue::SampleKind kind, const void* raw, const double* frequencies, size_t nBuffers,
+               uint32_t buffersPerSweep, uint32_t sampleRate, uint32_t sampleCount);
+  bool GetNextSamples(SampleQueue* sampleQueue, double_t& centerFrequency) override;
+  bool StartStreaming(uint32_t numIterations, SampleQueue& sampleQueue) override;
+  void ThreadWorker() override;
+  double Retune(double frequency) override;
+
+ private:
+  void Append(SampleQueue* q, size_t b);
+  SampleQueue::SampleKind m_kind;
+  const char* m_raw;
+  const double* m_frequencies;
+  size_t m_nBuffers;
+  uint32_t m_buffersPerSweep;
+  size_t m_next = 0;
+  size_t m_bufferBytes;
+};

@@ -1,0 +1,138 @@
+// host_selftest -- CPU-only checks of the plugin-surface plumbing (no GPU calls): FrequencyTable
+// iteration, SampleQueue semantics (first-sweep drop, sequence ids, FIFO, bounded blocking, batch
+// multiples, raw layout per kind), SyntheticSource determinism, SampleBuffer visitor protocol.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "buffer.h"
+#include "frequencyTable.h"
+#include "sampleBuffer.h"
+#include "sampleQueue.h"
+#include "syntheticSource.h"
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
+
+struct CountingVisitor : ProcessInterface<uint8_t> {
+  int begins = 0, ends = 0; uint64_t seq = 0; uint32_t total = 0, seen = 0, blocks = 0;
+  CountingVisitor() : ProcessInterface<uint8_t>(false) {}
+  void Begin(uint64_t s, uint32_t t) override { begins++; seq = s; total = t; seen = 0; blocks = 0; }
+  void Process(const uint8_t*, uint32_t c) override { seen += c; blocks++; }
+  void End() override { ends++; CHECK(seen == total); }
+};
+
+int main() {
+  // ---- FrequencyTable (frequencyTable.cpp:9-47)
+  FrequencyTable ft(20000000, 2.4e9, 3.15e9, 0.75, 0.0, false);
+  CHECK(ft.GetFrequencyCount() == 50);
+  CHECK(ft.GetCurrentFrequency() == 2407500000.0 && ft.GetIsScanStart());
+  CHECK(ft.GetNextFrequency() == 2422500000.0 && !ft.GetIsScanStart());
+  for (int i = 0; i < 49; i++) ft.GetNextFrequency();
+  CHECK(ft.GetIsScanStart() && ft.GetIterationCount() == 1 && ft.GetCurrentFrequency() == 2407500000.0);
+  CHECK(ft.GetStartFrequency() == 2407500000.0 && ft.GetStopFrequency() == 2407500000.0 + 49 * 15e6);
+  FrequencyTable one(8000000, 3e8, 0.0, 0.75, 0.0, false);
+  CHECK(one.GetFrequencyCount() == 1 && one.GetCurrentFrequency() == 303000000.0);
+  one.GetNextFrequency();
+  CHECK(one.GetIterationCount() == 1 && one.GetIsScanStart());
+
+  // ---- SampleQueue: first-sweep drop, sequence ids, FIFO, raw layout
+  {
+    const uint32_t N = 64;
+    SampleQueue q(SampleQueue::ShortComplex, 12, N, 8, false, false);
+    std::vector<int16_t> buf(2 * N);
+    for (int b = 0; b < 9; b++) {                       // 3 sweeps of 3 buffers
+      for (uint32_t i = 0; i < 2 * N; i++) buf[i] = int16_t(b * 100 + i);
+      q.AppendSamples(reinterpret_cast<int16_t(*)[2]>(buf.data()), 1e6 * b, (b % 3 == 0) ? time_t(1000 + b) : 0);
+    }
+    q.SetIsDone();
+    CHECK(q.GetDroppedCount() == 3 && q.GetAcceptedCount() == 6);       // messageQueue.h:67-72
+    for (int b = 3; b < 9; b++) {
+      SampleQueue::MessageType* m = q.GetNextSamples();
+      CHECK(m != nullptr);
+      CHECK(m->GetHeader().m_sequenceId == uint64_t(b - 3));
+      CHECK(m->GetHeader().m_frequency == 1e6 * b);
+      CHECK((m->GetHeader().m_time != 0) == (b % 3 == 0));
+      CHECK(static_cast<int16_t*>(m->GetData())[5] == int16_t(b * 100 + 5));
+      CHECK(m->GetDataBytes() == 4 * N);
+      q.MessageProcessed(m);
+    }
+    CHECK(q.GetNextSamples() == nullptr && q.GetIsDone());
+  }
+  {
+    // split int16 -> re block then im block; int8 and float pass through
+    const uint32_t N = 32;
+    SampleQueue q(SampleQueue::Short, 12, N, 4, false, false);
+    q.SetDropFirstSweep(false);
+    std::vector<int16_t> re(N), im(N);
+    for (uint32_t i = 0; i < N; i++) { re[i] = int16_t(i); im[i] = int16_t(-int(i)); }
+    q.AppendSamples(re.data(), im.data(), 5.0, 0);
+    auto* m = q.GetNextSamples();
+    const int16_t* d = static_cast<const int16_t*>(m->GetData());
+    CHECK(d[3] == 3 && d[N + 3] == -3);
+    q.MessageProcessed(m);
+    q.SetIsDone();
+  }
+  {
+    // bounded: the producer blocks at bufferCount and resumes as the consumer drains; batch multiples
+    const uint32_t N = 16;
+    SampleQueue q(SampleQueue::ByteComplex, 8, N, 4, true, false);
+    q.SetDropFirstSweep(false);
+    std::atomic<int> appended{0};
+    std::thread producer([&] {
+      std::vector<int8_t> buf(2 * N, 1);
+      for (int b = 0; b < 10; b++) { q.AppendSamples(reinterpret_cast<int8_t(*)[2]>(buf.data()), b, 0); appended++; }
+      q.SetIsDone();
+    });
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    CHECK(appended == 4);                                 // queue depth 4 reached, producer parked
+    std::vector<SampleQueue::MessageType*> batch;
+    uint64_t next = 0; uint32_t total = 0;
+    while (uint32_t n = q.GetNextBatch(batch, 4, 2)) {
+      if (!q.GetIsDone()) CHECK(n % 2 == 0);
+      for (auto* m : batch) { CHECK(m->GetHeader().m_sequenceId == next++); q.MessageProcessed(m); }
+      total += n;
+    }
+    producer.join();
+    CHECK(total == 10);
+    CHECK(!q.ReceivedAck()); q.SendAck(); CHECK(q.ReceivedAck()); q.ClearAck(); CHECK(!q.ReceivedAck());
+  }
+
+  // ---- SyntheticSource: deterministic, kind layouts, drives a queue through sweeps
+  {
+    const uint32_t N = 256;
+    SyntheticSource a(SampleQueue::ByteComplex, 8, 42, 2, 20000000, N, 2.4e9, 2.45e9);
+    SyntheticSource b(SampleQueue::ByteComplex, 8, 42, 2, 20000000, N, 2.4e9, 2.45e9);
+    std::vector<int8_t> x(2 * N), y(2 * N), z(2 * N);
+    a.Generate(1, 2, 0, x.data()); b.Generate(1, 2, 0, y.data()); a.Generate(1, 2, 1, z.data());
+    CHECK(memcmp(x.data(), y.data(), 2 * N) == 0 && memcmp(x.data(), z.data(), 2 * N) != 0);
+    CHECK(a.GetFrequencyCount() == 3);
+    SampleQueue q(SampleQueue::ByteComplex, 8, N, 64, true, false);
+    a.Start();
+    a.StartStreaming(3, q);                             // 3 sweeps x 3 steps x 2 buffers, first sweep dropped
+    uint32_t got = 0, starts = 0;
+    while (auto* m = q.GetNextSamples()) { got++; starts += m->GetHeader().m_time != 0; q.MessageProcessed(m); }
+    a.Join();
+    CHECK(got == 12 && starts == 2 && q.GetDroppedCount() == 6);
+  }
+
+  // ---- SampleBuffer + visitor protocol (buffer.cpp:360-372: one Begin, one Process per block, one End)
+  {
+    const uint32_t N = 128;
+    SampleBuffer sb(SampleBuffer::ShortComplex, 12, N, 8);
+    std::vector<int16_t> buf(2 * N, 7);
+    for (int b = 0; b < 5; b++) sb.AppendSamples(reinterpret_cast<int16_t(*)[2]>(buf.data()), 100.0 + b);
+    sb.SetIsDone();
+    CountingVisitor v;
+    std::vector<double> f;
+    CHECK(sb.GetNextSamples(&v, f, 3) == 3 && v.begins == 1 && v.ends == 1 && v.blocks == 3 && v.seq == 0);
+    CHECK(v.total == 3 * 4 * N && f.size() == 3 && f[2] == 102.0);
+    CHECK(sb.GetNextSamples(&v, f, 3) == 2 && v.seq == 3 * N && f[0] == 103.0);
+    CHECK(sb.GetNextSamples(&v, f, 3) == 0);
+  }
+  printf("host_selftest ok\n");
+  return 0;
+}

@@ -1,0 +1,130 @@
+// scan_b200 -- wires source -> SampleQueue -> ProcessSamples the way the reference's main() does
+// (scan.cpp:137-239), with the GPU consumer.  No SDR SDKs: the source is synthetic or a replay.
+//
+//   scan_b200 replay <kind> <N> <fs> <enob> <dc> <threshold> <win_type> <mode> <buffers_per_sweep>
+//                    <raw_file> <freq_file> [threads] [legacy]
+//       same arguments and input files as oracle/_ref/ref_tool scan; prints what the reference prints.
+//       "legacy" routes through SampleBuffer + GpuProcessInterface instead of SampleQueue.
+//   scan_b200 synth <kind> <N> <fs> <enob> <dc> <threshold> <start> <stop> <buffers_per_step>
+//                   <iterations> <seed> [threads] [averaging]
+//       seeded SyntheticSource sweep (first sweep dropped like the reference: needs iterations >= 2).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "buffer.h"
+#include "process.h"
+#include "sampleBuffer.h"
+#include "sampleQueue.h"
+#include "syntheticSource.h"
+
+static std::vector<char> ReadFile(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
+  std::vector<char> data;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  return data;
+}
+
+static int RunLegacy(int kind, uint32_t n, uint32_t fs, uint32_t enob, bool dc, float thr, int win,
+                     const std::vector<char>& raw, const double* freqs, size_t nbuf) {
+  // SampleBuffer + GpuProcessInterface: the legacy surface named by north_star.
+  SampleBuffer::SampleKind sk = kind == SCN_KIND_SHORT ? SampleBuffer::Short
+                              : kind == SCN_KIND_SHORT_COMPLEX ? SampleBuffer::ShortComplex : SampleBuffer::FloatComplex;
+  SampleBuffer sb(sk, enob, n, 64);
+  std::vector<float> window(n);
+  scn_window_build(win, n, window.data());
+  scn_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.sample_count = n; cfg.sample_rate = fs; cfg.enob = enob; cfg.sample_kind = sb.GetScnKind();
+  cfg.correct_dc_offset = dc; cfg.averaging = 1; cfg.threshold = thr;
+  cfg.use_window = scn_use_window(0.75, n); cfg.dc_ignore_window = 4; cfg.window = window.data();
+  cfg.max_spectra = 16; cfg.flags = 0;
+  scn_ctx* ctx = nullptr;
+  if (scn_create(&cfg, &ctx) != SCN_OK) { fprintf(stderr, "scn_create: %s\n", scn_last_error()); return 1; }
+  std::thread producer([&] {
+    const size_t bb = sb.GetBufferBytes();
+    for (size_t b = 0; b < nbuf; b++) {
+      char* p = const_cast<char*>(raw.data()) + b * bb;
+      if (sk == SampleBuffer::Short) sb.AppendSamples(reinterpret_cast<int16_t*>(p), reinterpret_cast<int16_t*>(p) + n, freqs[b]);
+      else if (sk == SampleBuffer::ShortComplex) sb.AppendSamples(reinterpret_cast<int16_t(*)[2]>(p), freqs[b]);
+      else sb.AppendSamples(reinterpret_cast<fftwf_complex*>(p), freqs[b]);
+    }
+    sb.SetIsDone();
+  });
+  GpuProcessInterface gpu(ctx, 16, 1, n);
+  std::vector<double> f;
+  const uint32_t words = scn_mask_words(ctx);
+  while (uint32_t got = sb.GetNextSamples(&gpu, f, 16)) {
+    for (uint32_t s = 0; s < got; s++)
+      for (uint32_t i = 0; i < n; i++)
+        if (gpu.GetHitMasks()[size_t(s) * words + (i >> 5)] >> (i & 31) & 1u)
+          printf("freq %lu\n", (unsigned long)scn_hit_frequency(f[s], fs, n, i));
+  }
+  producer.join();
+  scn_destroy(ctx);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: scan_b200 <replay|synth> ...\n"); return 2; }
+  const std::string cmd = argv[1];
+  if (cmd == "replay" && argc >= 13) {
+    const int kind = atoi(argv[2]);
+    const uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    const bool dc = atoi(argv[6]) != 0;
+    const float thr = float(atof(argv[7]));
+    const int win = atoi(argv[8]), mode = atoi(argv[9]);
+    const uint32_t perSweep = atoi(argv[10]);
+    std::vector<char> raw = ReadFile(argv[11]);
+    std::vector<char> fr = ReadFile(argv[12]);
+    const uint32_t threads = argc > 13 ? atoi(argv[13]) : 1;
+    const bool legacy = argc > 14 && std::string(argv[14]) == "legacy";
+    const size_t bb = SyntheticSource::BufferBytes(SampleQueue::SampleKind(kind), n);
+    const size_t nbuf = raw.size() / bb;
+    const double* freqs = reinterpret_cast<const double*>(fr.data());
+    if (legacy) return RunLegacy(kind, n, fs, enob, dc, thr, win, raw, freqs, nbuf);
+    ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs, nbuf, perSweep, fs, n);
+    ProcessSamples process(n, fs, enob, thr, win, ProcessSamples::Mode(mode), threads);
+    SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
+    source.Start();
+    source.StartStreaming(1, queue);
+    process.StartProcessing(queue);
+    source.Join();
+    fflush(stdout);
+    return 0;
+  }
+  if (cmd == "synth" && argc >= 13) {
+    const int kind = atoi(argv[2]);
+    const uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    const bool dc = atoi(argv[6]) != 0;
+    const float thr = float(atof(argv[7]));
+    const double start = atof(argv[8]), stop = atof(argv[9]);
+    const uint32_t perStep = atoi(argv[10]), iterations = atoi(argv[11]);
+    const uint64_t seed = strtoull(argv[12], nullptr, 0);
+    const uint32_t threads = argc > 13 ? atoi(argv[13]) : 2;       // the reference runs 2 (scan.cpp:217)
+    const uint32_t averaging = argc > 14 ? atoi(argv[14]) : 1;
+    SyntheticSource source(SampleQueue::SampleKind(kind), enob, seed, perStep, fs, n, start, stop);
+    ProcessSamples process(n, fs, enob, thr, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
+    process.SetAveraging(averaging);
+    SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
+    const auto t0 = std::chrono::steady_clock::now();
+    source.Start();
+    source.StartStreaming(iterations, queue);
+    process.StartProcessing(queue);
+    source.Join();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    printf("Elapsed time = %f ms\n", ms);                         // scan.cpp:43-47
+    fprintf(stderr, "buffers %lu hits %lu launches %lu\n", (unsigned long)process.GetBuffersProcessed(),
+            (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount());
+    return 0;
+  }
+  fprintf(stderr, "scan_b200: bad arguments\n");
+  return 2;
+}

@@ -1,0 +1,85 @@
+"""The C++ plugin surface (SignalSource / SampleQueue / ProcessSamples / ProcessInterface /
+SampleBuffer under scanner_b200/csrc/host).  CPU: plumbing selftest.  GPU: scan_b200 (source ->
+queue -> GPU ProcessSamples) must print what the reference prints for the same raw buffers."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import golden_util as GU
+from tests.conftest import ROOT
+
+G = GU.load()
+TOOL = os.path.join(ROOT, "scanner_b200", "scan_b200")
+SELFTEST = os.path.join(ROOT, "scanner_b200", "host_selftest")
+
+
+def test_host_selftest_cpu():
+    out = subprocess.run([SELFTEST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=60)
+    assert out.returncode == 0, out.stdout.decode()
+    assert b"host_selftest ok" in out.stdout
+
+
+def run_replay(case, threads=1, legacy=False):
+    with tempfile.TemporaryDirectory() as d:
+        rp, fp = os.path.join(d, "raw.bin"), os.path.join(d, "freq.bin")
+        np.ascontiguousarray(case["raw"]).tofile(rp)
+        np.ascontiguousarray(case["freqs"], np.float64).tofile(fp)
+        cmd = [TOOL, "replay", str(case["kind"]), str(case["n"]), repr(float(case["fs"])), str(case["enob"]),
+               "1" if case["dc"] else "0", repr(case["thr"]), str(case["win"]), str(case["mode"]),
+               str(0 if legacy else case["per_sweep"]), rp, fp, str(threads)] + (["legacy"] if legacy else [])
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        assert out.returncode == 0, out.stderr.decode()
+        return out.stdout.decode()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in GU.scan_cases(G) if c["n"] >= 256], ids=lambda c: c["name"])
+def test_scan_b200_prints_what_the_reference_prints(case):
+    text = run_replay(case)
+    want = case["text"]
+    if case["mode"] == 2:
+        got_hits, want_hits = GU.parse_hits(text), GU.parse_hits(want)
+        assert [f for f, _ in got_hits] == [f for f, _ in want_hits] and want_hits
+        assert max(abs(a - b) for (_, a), (_, b) in zip(got_hits, want_hits)) < 1e-3 + 1e-6
+    else:
+        got_td, want_td = GU.parse_time_domain(text), GU.parse_time_domain(want)
+        assert [(s, f) for s, _, f, _ in got_td] == [(s, f) for s, _, f, _ in want_td] and want_td
+        assert all(abs(a[1] - b[1]) < 1e-5 and abs(a[3] - b[3]) < 1e-5 for a, b in zip(got_td, want_td))
+    # same line structure: thread banners and one "Start scan at" per accepted sweep
+    # (the golden run drives the reference's queue + ProcessSamples without a SignalSource, so the
+    #  source-side banners -- table dump, "Starting source thread" -- are not part of it)
+    strip = lambda t: [re.sub(r"power_db .*|Max signal .*|Start scan at .*", "", l) for l in t.splitlines()
+                       if not re.match(r"Frequency \d+:|Starting source thread|Stopping source thread", l)]
+    assert strip(text) == strip(want)
+
+
+@pytest.mark.gpu
+def test_legacy_samplebuffer_visitor_path():
+    case = next(c for c in GU.scan_cases(G) if c["name"] == "i16_dc_512")
+    text = run_replay(case, legacy=True)            # SampleBuffer has no first-sweep drop
+    freqs = [int(m.group(1)) for m in re.finditer(r"freq (\d+)", text)]
+    want = [f for f, _ in GU.parse_hits(case["text"])]
+    assert len(freqs) > len(want) and freqs[-len(want):] == want
+
+
+@pytest.mark.gpu
+def test_synthetic_source_sweep_two_workers():
+    # 3 sweeps x 4 steps x 8 buffers through 2 consumer threads (the reference's thread count)
+    out = subprocess.run([TOOL, "synth", "1", "2048", "20000000", "8", "1", "30.0", "2.4e9", "2.46e9", "8", "3", "7", "2"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert out.returncode == 0, out.stderr.decode()
+    m = re.search(r"buffers (\d+) hits (\d+) launches (\d+)", out.stderr.decode())
+    assert m and int(m.group(1)) == 2 * 4 * 8 and int(m.group(3)) >= 1
+    text = out.stdout.decode()
+    assert text.count("Start scan at") == 2 and "Elapsed time" in text
+    assert len(GU.parse_hits(text)) == int(m.group(2))
+    # K = 4 averaging: 64 buffers -> 16 spectra
+    out = subprocess.run([TOOL, "synth", "1", "2048", "20000000", "8", "1", "30.0", "2.4e9", "2.46e9", "8", "3", "7", "1", "4"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert out.returncode == 0, out.stderr.decode()
+    m = re.search(r"buffers (\d+) hits (\d+) launches (\d+)", out.stderr.decode())
+    assert m and int(m.group(1)) == 64
