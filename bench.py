@@ -291,8 +291,8 @@ def main() -> None:
     spectra_per_step_per_gpu = max(1, wl["buffers_per_step"] // K)
     units_per_step = spectra_per_step_per_gpu * world          # dwell grows with N (weak scaling)
     total_units = units_per_step * n_steps
-    first_unit, end_unit = S.shard_steps(total_units, rank, world)
-    n_spectra = end_unit - first_unit
+    shard = S.plan_shard(n_steps, units_per_step, rank, world)
+    first_unit, n_spectra = shard.first_unit, shard.n_units
     n_buffers = n_spectra * K
     samples_per_rank = n_buffers * n
 
@@ -329,7 +329,7 @@ def main() -> None:
         ctx.summarize_steps(d_mask.data_ptr(), d_count.data_ptr(), n_spectra, first_unit, units_per_step,
                             n_steps, d_rec.data_ptr(), sh)
         if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_rec)
+            S.gather_step_records(d_rec, world, out=d_gather)       # NCCL all-gather of ~13 KB per rank
             ctx.merge_step_records(d_gather.data_ptr(), world, n_steps, d_merged.data_ptr(), sh)
 
     def barrier() -> None:

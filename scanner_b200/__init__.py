@@ -13,3 +13,4 @@ from .binding import (  # noqa: F401
     use_window, hit_frequency, frequency_table, window_build, shard_steps,
     bytes_per_sample,
 )
+from .sweep import ShardPlan, plan_shard, gather_step_records  # noqa: F401,E402
