@@ -108,24 +108,20 @@ int ilog2_exact(uint32_t n) {
   return l;
 }
 
-// Twiddle tables of the Stockham plan (scn_fft.cuh): for pass p >= 1, butterfly j = t + m*T,
-// k = j mod Ns, factor r: W_{Ns*R}^{k*r} = exp(-2 pi i k r / (Ns R)), evaluated in double.
+// Twiddle tables of the Stockham plan (scn_fft.cuh): passes p >= 1 are radix 16; thread t of pass p
+// multiplies input r by W_{16 Ns}^{k r} = exp(-2 pi i k r / (16 Ns)), k = t mod Ns, Ns = product of the
+// earlier radices.  Evaluated in double, stored thread-contiguous: tw[((p-1)*15 + r-1)*T + t].
 std::vector<float2> build_twiddles(int log2n) {
   const int N = 1 << log2n, T = N / 16;
   std::vector<float2> tw(size_t(scn::total_tw_per_thread(log2n)) * T);
   for (int p = 1; p < scn::num_passes(log2n); p++) {
-    const int log2r = scn::pass_log2r(log2n, p);
-    const int R = 1 << log2r, M = 16 / R;
-    const int Ns = 1 << (4 * p);
-    const int off = scn::pass_tw_offset(log2n, p);
-    for (int m = 0; m < M; m++)
-      for (int r = 1; r < R; r++)
-        for (int t = 0; t < T; t++) {
-          const int j = t + m * T;
-          const int k = j & (Ns - 1);
-          const double a = -2.0 * kPi * double(k) * double(r) / (double(Ns) * double(R));
-          tw[size_t(off + m * (R - 1) + (r - 1)) * T + t] = make_float2(float(std::cos(a)), float(std::sin(a)));
-        }
+    const int Ns = 1 << scn::pass_log2ns(log2n, p);
+    for (int r = 1; r < 16; r++)
+      for (int t = 0; t < T; t++) {
+        const int k = t & (Ns - 1);
+        const double a = -2.0 * kPi * double(k) * double(r) / (16.0 * double(Ns));
+        tw[size_t((p - 1) * 15 + (r - 1)) * T + t] = make_float2(float(std::cos(a)), float(std::sin(a)));
+      }
   }
   return tw;
 }
@@ -309,7 +305,7 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
   auto bail = [&](int code) { scn_destroy(c); return code; };
 
   if (!td) {
-    if (!scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, &c->variant))
+    if (!scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant))
       return bail(fail(SCN_ERR_INVALID, "no kernel variant for kind %u, N %u", cf.sample_kind, cf.sample_count));
     e = cudaFuncSetAttribute(c->variant.func, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(c->variant.smem_bytes));

@@ -17,24 +17,25 @@ struct KernelVariant {
 };
 
 // One translation unit per sample kind (compiled in parallel); each fills its rows.
-bool variant_byte_complex(int log2n, bool dc, KernelVariant* out);
-bool variant_short(int log2n, bool dc, KernelVariant* out);
-bool variant_short_complex(int log2n, bool dc, KernelVariant* out);
-bool variant_float_complex(int log2n, bool dc, KernelVariant* out);
+bool variant_byte_complex(int log2n, bool dc, bool avg, KernelVariant* out);
+bool variant_short(int log2n, bool dc, bool avg, KernelVariant* out);
+bool variant_short_complex(int log2n, bool dc, bool avg, KernelVariant* out);
+bool variant_float_complex(int log2n, bool dc, bool avg, KernelVariant* out);
 
-inline bool find_variant(int kind, int log2n, bool dc, KernelVariant* out) {
+// avg: K > 1 (keeps the 16 accumulators live across the K loop; K == 1 kernels do not pay for them)
+inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* out) {
   switch (kind) {
-    case SCN_KIND_BYTE_COMPLEX: return variant_byte_complex(log2n, dc, out);
-    case SCN_KIND_SHORT: return variant_short(log2n, dc, out);
-    case SCN_KIND_SHORT_COMPLEX: return variant_short_complex(log2n, dc, out);
-    case SCN_KIND_FLOAT_COMPLEX: return variant_float_complex(log2n, false, out);
+    case SCN_KIND_BYTE_COMPLEX: return variant_byte_complex(log2n, dc, avg, out);
+    case SCN_KIND_SHORT: return variant_short(log2n, dc, avg, out);
+    case SCN_KIND_SHORT_COMPLEX: return variant_short_complex(log2n, dc, avg, out);
+    case SCN_KIND_FLOAT_COMPLEX: return variant_float_complex(log2n, false, avg, out);
     default: return false;
   }
 }
 
-#define SCN_VARIANT_CASE(L, KIND, DC, NAME)                                                   \
+#define SCN_VARIANT_CASE(L, KIND, DC, AVG, NAME)                                                   \
   case L: {                                                                                   \
-    out->func = reinterpret_cast<const void*>(&spectrum_sense_kernel<L, KIND, DC>);          \
+    out->func = reinterpret_cast<const void*>(&spectrum_sense_kernel<L, KIND, DC, AVG>);          \
     out->threads = Geometry<L>::THREADS;                                                      \
     out->smem_bytes = Geometry<L>::kSmemBytes;                                                \
     out->transforms_per_cta = Geometry<L>::F;                                                 \
@@ -42,15 +43,15 @@ inline bool find_variant(int kind, int log2n, bool dc, KernelVariant* out) {
     return true;                                                                              \
   }
 
-#define SCN_VARIANT_TABLE(KIND, DC, NAME)                                                     \
+#define SCN_VARIANT_TABLE(KIND, DC, AVG, NAME)                                                     \
   switch (log2n) {                                                                            \
-    SCN_VARIANT_CASE(8, KIND, DC, NAME)                                                       \
-    SCN_VARIANT_CASE(9, KIND, DC, NAME)                                                       \
-    SCN_VARIANT_CASE(10, KIND, DC, NAME)                                                      \
-    SCN_VARIANT_CASE(11, KIND, DC, NAME)                                                      \
-    SCN_VARIANT_CASE(12, KIND, DC, NAME)                                                      \
-    SCN_VARIANT_CASE(13, KIND, DC, NAME)                                                      \
-    SCN_VARIANT_CASE(14, KIND, DC, NAME)                                                      \
+    SCN_VARIANT_CASE(8, KIND, DC, AVG, NAME)                                                       \
+    SCN_VARIANT_CASE(9, KIND, DC, AVG, NAME)                                                       \
+    SCN_VARIANT_CASE(10, KIND, DC, AVG, NAME)                                                      \
+    SCN_VARIANT_CASE(11, KIND, DC, AVG, NAME)                                                      \
+    SCN_VARIANT_CASE(12, KIND, DC, AVG, NAME)                                                      \
+    SCN_VARIANT_CASE(13, KIND, DC, AVG, NAME)                                                      \
+    SCN_VARIANT_CASE(14, KIND, DC, AVG, NAME)                                                      \
     default: return false;                                                                    \
   }
 

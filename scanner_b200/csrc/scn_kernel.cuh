@@ -1,10 +1,10 @@
 // scn_kernel.cuh -- the fused spectrum-sense kernel (sm_100a).
 //
-// One persistent CTA walks "groups" of F spectra (F = transforms resident in one CTA);
-// for each spectrum it streams K raw IQ buffers through
+// One persistent CTA walks "groups" of F spectra (F = transforms resident in one CTA); for each
+// spectrum it streams K raw IQ buffers through
 //   load -> [DC sum] -> convert+scale+window -> FFT -> |X|^2 -> accumulate
-// entirely in registers/shared memory, then emits dB, the detection mask, the hit
-// count and the compact hit records.  Each raw sample crosses HBM exactly once.
+// entirely in registers/shared memory, then emits dB, the detection mask, the hit count and the
+// compact hit records.  Each raw sample crosses HBM exactly once.
 //
 // Reference arithmetic restated (file:line under the reference tree):
 //   conversion      utility.cpp:34-56 (int8), :58-84 (int16 interleaved), :9-32 (int16 split)
@@ -13,7 +13,12 @@
 //   FFT             fft.cpp:20-25      (forward, unnormalised)
 //   dB              utility.cpp:91-97  (10*log2(sqrt(re^2+im^2))/log2(10))
 //   detection       process.cpp:46-61  (fftshift index, DC hole, used band, strict >)
-//   time domain     process.cpp:203-237
+//
+// Software pipeline of one tile (= one raw buffer of one transform group):
+//   convert raw(t) -> issue loads raw(t+1) -> pass 0 -> exchange -> ... -> [DC partial sums of
+//   raw(t+1) into smem] -> last exchange barrier -> [dc(t+1) from smem] -> last pass -> power.
+// The next tile's HBM latency hides behind this tile's FFT, and the DC reduction rides on an
+// exchange barrier that is needed anyway.  Barriers per tile: (passes - 1) + 1 per spectrum.
 #pragma once
 #include "scn_fft.cuh"
 #include "../../include/scanner_b200.h"
@@ -39,6 +44,9 @@ struct KernelParams {
 
 // dB = 10*log2(sqrt(p))/log2(10) = (5/log2(10)) * log2(p)
 constexpr float kDbPerLog2 = 1.5051499783199060f;
+// 1.5 * 2^23: float(kMagic | u) == 12582912 + u for 0 <= u < 2^22
+constexpr uint32_t kMagicBits = 0x4B400000u;
+constexpr float kMagic = 12582912.0f;
 
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<SCN_KIND_BYTE_COMPLEX> { static constexpr int kBytes = 2; static constexpr bool kInt = true; };
@@ -56,50 +64,192 @@ struct Geometry {
   static constexpr int WORDS = N / 32;                            // mask words per spectrum
   static constexpr int WARPS = THREADS / 32;
   static constexpr int WARPS_PER_FFT = (T >= 32) ? T / 32 : 1;
+  static constexpr int FFTS_PER_WARP = (T >= 32) ? 1 : 32 / T;
   // Two exchange tiles (ping-pong: one barrier per exchange) whenever they leave room for
   // several CTAs per SM; the largest size falls back to one tile and two barriers.
   static constexpr int XBUFS = (LOG2N <= 13) ? 2 : 1;
   static constexpr size_t kXchTile = sizeof(float2) * size_t(xch_elems(N)) * F;
   static constexpr size_t kXchBytes = kXchTile * XBUFS;
+  static constexpr size_t kMaskBytes = sizeof(uint32_t) * size_t(WORDS) * F * 2;   // ping-pong by spectrum parity
+  static constexpr int RED_SLOTS = (WARPS > F) ? WARPS : F;                        // (si, sq) pairs per parity
+  static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * RED_SLOTS * 2;         // ping-pong by tile parity
+  static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes;
   // register budget: 128/thread up to 512-thread CTAs
   static constexpr int MIN_CTAS = (THREADS <= 128) ? 4 : (THREADS <= 256 ? 2 : 1);
-  static constexpr size_t kMaskBytes = sizeof(uint32_t) * size_t(WORDS) * F * 2;   // mask + prefix
-  static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * WARPS;
-  static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes;
 };
 
-// Raw sample fetch: integer I,Q of sample n of the buffer at `buf`.
-template <int KIND, int N>
-__device__ __forceinline__ void load_raw_int(const uint8_t* __restrict__ buf, int n, int& i, int& q) {
-  if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) {
-    const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(buf) + n);
-    i = static_cast<int>(static_cast<signed char>(u & 0xff));
-    q = static_cast<int>(static_cast<signed char>(u >> 8));
-  } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
-    const unsigned int u = __ldg(reinterpret_cast<const unsigned int*>(buf) + n);
-    i = static_cast<int>(static_cast<short>(u & 0xffff));
-    q = static_cast<int>(static_cast<short>(u >> 16));
-  } else {   // SCN_KIND_SHORT: re[N] then im[N]
-    const short* p = reinterpret_cast<const short*>(buf);
-    i = static_cast<int>(__ldg(p + n));
-    q = static_cast<int>(__ldg(p + N + n));
-  }
-}
+// ---- raw tile of one thread ----------------------------------------------------------------------
+// Row r of pass 0 is M0 consecutive samples starting at sample M0*t + r*(N/R0).
+template <int LOG2N, int KIND>
+struct RawTile {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2R0 = pass_log2r(LOG2N, 0);
+  static constexpr int R0 = 1 << LOG2R0, M0 = 16 / R0;
+  static constexpr int kBytes = KindTraits<KIND>::kBytes;
+  static constexpr bool kSplit = KIND == SCN_KIND_SHORT;
+  // bytes of one contiguous run: M0 samples (or M0 int16 for each half of the split layout)
+  static constexpr int RUN = kSplit ? M0 * 2 : M0 * kBytes;
+  static constexpr int WPR = (RUN + 3) / 4;                       // 32-bit words per run
+  static constexpr int RUNS = kSplit ? 2 : 1;
+  static constexpr int WORDS = R0 * RUNS * WPR;                   // raw registers per thread
+  uint32_t w[WORDS];
 
-template <int LOG2N, int KIND, bool DC>
+  template <int NB>
+  static __device__ __forceinline__ void load_run(const uint8_t* __restrict__ p, uint32_t* dst) {
+    if constexpr (NB == 2) {
+      dst[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
+    } else if constexpr (NB == 4) {
+      dst[0] = __ldg(reinterpret_cast<const unsigned int*>(p));
+    } else if constexpr (NB == 8) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+      dst[0] = v.x; dst[1] = v.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB / 16; i++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ buf, int t) {
+#pragma unroll
+    for (int r = 0; r < R0; r++) {
+      const int s0 = M0 * t + r * (N / R0);
+      if constexpr (kSplit) {
+        load_run<RUN>(buf + size_t(s0) * 2, &w[(r * 2) * WPR]);
+        load_run<RUN>(buf + size_t(N) * 2 + size_t(s0) * 2, &w[(r * 2 + 1) * WPR]);
+      } else {
+        load_run<RUN>(buf + size_t(s0) * kBytes, &w[r * WPR]);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < WORDS; i++) w[i] = 0u;
+  }
+
+  // int32 sums of I and Q over this thread's 16 samples (utility.cpp:44-48), packed dot products.
+  __device__ __forceinline__ void sums(int& si, int& sq) const {
+    si = 0; sq = 0;
+#pragma unroll
+    for (int r = 0; r < R0; r++) {
+#pragma unroll
+      for (int x = 0; x < WPR; x++) {
+        if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) {
+          const int v = int(w[r * WPR + x]);
+          if constexpr (RUN == 2) {          // one sample: I in byte 0, Q in byte 1
+            si = __dp4a(v, 0x00000001, si);
+            sq = __dp4a(v, 0x00000100, sq);
+          } else {
+            si = __dp4a(v, 0x00010001, si);
+            sq = __dp4a(v, 0x01000100, sq);
+          }
+        } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
+          const int v = int(w[r * WPR + x]);
+          si = __dp2a_lo(v, 0x00000001, si);
+          sq = __dp2a_lo(v, 0x00000100, sq);
+        } else if constexpr (KIND == SCN_KIND_SHORT) {
+          const int a = int(w[(r * 2) * WPR + x]), b = int(w[(r * 2 + 1) * WPR + x]);
+          const int sel = (RUN == 2) ? 0x00000001 : 0x00000101;   // one or two int16 per word
+          si = __dp2a_lo(a, sel, si);
+          sq = __dp2a_lo(b, sel, sq);
+        }
+      }
+    }
+  }
+
+  // Converted + windowed samples into register slots q = m + r*M0.
+  //   reference: float(int(x) - dc) * onebymax, then * window  (utility.cpp:52-55, process.cpp:28-34)
+  //   here: onebymax is folded into w (exact, a power of two).  Fast path: the integer is placed in
+  //   the mantissa of 1.5*2^23 (PRMT), one exact FADD2 removes the magic, the offset and dc, one
+  //   FMUL2 applies the window -- bit-identical to int subtract -> I2F -> multiply while
+  //   |dc| <= 2^21.  Slow path (the unsigned-division quirk can make dc ~ 2^32/N): integer
+  //   subtract and I2F, exactly as written in the reference.
+  __device__ __forceinline__ void convert(float2 (&v)[kPts], const float (&win)[kPts], int dci, int dcq) const {
+    if constexpr (KIND == SCN_KIND_FLOAT_COMPLEX) {
+#pragma unroll
+      for (int r = 0; r < R0; r++)
+#pragma unroll
+        for (int m = 0; m < M0; m++) {
+          const int q = m + r * M0;
+          const float2 x = make_float2(__uint_as_float(w[r * WPR + 2 * m]), __uint_as_float(w[r * WPR + 2 * m + 1]));
+          v[q] = __fmul2_rn(x, make_float2(win[q], win[q]));
+        }
+    } else {
+      constexpr bool k8 = KIND == SCN_KIND_BYTE_COMPLEX;
+      constexpr float kOff = k8 ? 128.0f : 32768.0f;
+      const bool fast = (dci >= -(1 << 21)) && (dci <= (1 << 21)) && (dcq >= -(1 << 21)) && (dcq <= (1 << 21));
+      if (fast) {
+        const float2 negc = make_float2(-(kMagic + kOff + float(dci)), -(kMagic + kOff + float(dcq)));
+#pragma unroll
+        for (int r = 0; r < R0; r++)
+#pragma unroll
+          for (int m = 0; m < M0; m++) {
+            const int q = m + r * M0;
+            uint32_t bi, bq;
+            if constexpr (k8) {
+              const uint32_t x = w[r * WPR + (m >> 1)] ^ 0x80808080u;
+              bi = __byte_perm(x, kMagicBits, 0x7650 + 2 * (m & 1));
+              bq = __byte_perm(x, kMagicBits, 0x7651 + 2 * (m & 1));
+            } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
+              const uint32_t x = w[r * WPR + m] ^ 0x80008000u;
+              bi = __byte_perm(x, kMagicBits, 0x7610);
+              bq = __byte_perm(x, kMagicBits, 0x7632);
+            } else {
+              const uint32_t xa = w[(r * 2) * WPR + (m >> 1)] ^ 0x80008000u;
+              const uint32_t xb = w[(r * 2 + 1) * WPR + (m >> 1)] ^ 0x80008000u;
+              bi = __byte_perm(xa, kMagicBits, (m & 1) ? 0x7632 : 0x7610);
+              bq = __byte_perm(xb, kMagicBits, (m & 1) ? 0x7632 : 0x7610);
+            }
+            const float2 d = __fadd2_rn(make_float2(__uint_as_float(bi), __uint_as_float(bq)), negc);
+            v[q] = __fmul2_rn(d, make_float2(win[q], win[q]));
+          }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R0; r++)
+#pragma unroll
+          for (int m = 0; m < M0; m++) {
+            const int q = m + r * M0;
+            int xi, xq;
+            if constexpr (k8) {
+              const uint32_t x = w[r * WPR + (m >> 1)] >> (16 * (m & 1));
+              xi = int(static_cast<signed char>(x & 0xff));
+              xq = int(static_cast<signed char>((x >> 8) & 0xff));
+            } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
+              const uint32_t x = w[r * WPR + m];
+              xi = int(static_cast<short>(x & 0xffff));
+              xq = int(static_cast<short>(x >> 16));
+            } else {
+              xi = int(static_cast<short>((w[(r * 2) * WPR + (m >> 1)] >> (16 * (m & 1))) & 0xffff));
+              xq = int(static_cast<short>((w[(r * 2 + 1) * WPR + (m >> 1)] >> (16 * (m & 1))) & 0xffff));
+            }
+            v[q].x = __fmul_rn(float(xi - dci), win[q]);
+            v[q].y = __fmul_rn(float(xq - dcq), win[q]);
+          }
+      }
+    }
+  }
+};
+
+template <int LOG2N, int KIND, bool DC, bool AVG>
 __global__ void __launch_bounds__(Geometry<LOG2N>::THREADS, Geometry<LOG2N>::MIN_CTAS)
 spectrum_sense_kernel(const KernelParams p) {
   using G = Geometry<LOG2N>;
+  using Raw = RawTile<LOG2N, KIND>;
   constexpr int N = G::N, T = G::T, F = G::F;
   constexpr int NP = num_passes(LOG2N);
   constexpr bool kInt = KindTraits<KIND>::kInt;
+  constexpr bool kDC = DC && kInt;
   constexpr size_t kBufBytes = size_t(N) * KindTraits<KIND>::kBytes;
+  constexpr int R0 = Raw::R0, M0 = Raw::M0;
+  static_assert(NP >= 2 && NP <= 4, "supported sizes: 2^5 .. 2^16 with 16 points per thread");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* xch_all = reinterpret_cast<float2*>(smem_raw);
-  uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + G::kXchBytes);     // [F][WORDS]
-  uint32_t* sprefix = smask + F * G::WORDS;                                     // [F][WORDS]
-  int32_t* sred = reinterpret_cast<int32_t*>(smem_raw + G::kXchBytes + G::kMaskBytes);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + G::kXchBytes);          // [2][F][WORDS]
+  int32_t* sred = reinterpret_cast<int32_t*>(smem_raw + G::kXchBytes + G::kMaskBytes);   // [2][RED_SLOTS][2]
 
   const int tid = threadIdx.x;
   const int f = tid / T;             // which resident transform
@@ -109,12 +259,14 @@ spectrum_sense_kernel(const KernelParams p) {
   float2* xch0 = xch_all + size_t(f) * xch_elems(N);
   float2* xch1 = (G::XBUFS == 2) ? xch0 + size_t(F) * xch_elems(N) : xch0;
 
-  // Window taps for this thread's 16 sample positions stay in registers for the whole launch.
-  float w[kPts];
+  // Window taps of this thread's 16 sample positions (slot q = m + r*M0) stay in registers.
+  float win[kPts];
 #pragma unroll
-  for (int q = 0; q < kPts; q++) w[q] = __ldg(p.window + t + q * T);
+  for (int r = 0; r < R0; r++)
+#pragma unroll
+    for (int m = 0; m < M0; m++) win[m + r * M0] = __ldg(p.window + M0 * t + m + r * (N / R0));
 
-  const uint32_t K = p.averaging;
+  const uint32_t K = AVG ? p.averaging : 1u;
   const uint32_t n_groups = (p.n_spectra + F - 1) / F;
   const uint32_t half = N / 2;
 
@@ -129,182 +281,228 @@ spectrum_sense_kernel(const KernelParams p) {
     cand = cand && !(i < (half - p.use_window) || i > (half + p.use_window));
     candbits |= (cand ? 1u : 0u) << q;
   }
-  uint32_t xsel = 0;   // ping-pong selector of the exchange tile
 
-  for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-    const uint32_t s = g * F + f;                 // this transform's spectrum
-    const bool live = s < p.n_spectra;
-    float acc[kPts];
+  // ---- tile stream of this CTA: (group, k) for group = blockIdx.x, +gridDim.x, ...; k = 0..K-1 ----
+  uint32_t g = blockIdx.x;
+  if (g >= n_groups) return;
+  uint32_t k = 0;
+  uint32_t xsel = 0;      // ping-pong selector of the exchange tile
+  uint32_t tpar = 0;      // tile parity (DC partial sums ping-pong)
+  uint32_t spar = 0;      // spectrum parity (mask ping-pong)
 
-    for (uint32_t k = 0; k < K; k++) {
-      const uint8_t* buf = p.raw + (size_t(live ? s : 0) * K + k) * kBufBytes;
-      float2 v[kPts];
+  auto tile_ptr = [&](uint32_t gg, uint32_t kk, bool& live) -> const uint8_t* {
+    const uint32_t s = gg * F + f;
+    live = s < p.n_spectra;
+    return p.raw + (size_t(live ? s : 0) * K + kk) * kBufBytes;
+  };
+  // DC block reduction, warp part: one (si, sq) slot per warp (T >= 32) or per transform (T < 32)
+  auto reduce_dc = [&](int si, int sq, int32_t* red) {
+    constexpr int SEG = (T < 32) ? T : 32;
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) {
+      si += __shfl_xor_sync(0xffffffffu, si, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if constexpr (T >= 32) {
+      if (lane == 0) { red[2 * warp] = si; red[2 * warp + 1] = sq; }
+    } else {
+      if (t == 0) { red[2 * f] = si; red[2 * f + 1] = sq; }
+    }
+  };
+  auto finish_dc = [&](const int32_t* red, int& odci, int& odcq) {
+    int si = 0, sq = 0;
+    if constexpr (T >= 32) {
+      const int w0 = f * G::WARPS_PER_FFT;
+#pragma unroll
+      for (int i = 0; i < G::WARPS_PER_FFT; i++) { si += red[2 * (w0 + i)]; sq += red[2 * (w0 + i) + 1]; }
+    } else {
+      si = red[2 * f]; sq = red[2 * f + 1];
+    }
+    // dc = int32(uint32(sum) / N): the unsigned division of utility.cpp:49-50, N = 2^LOG2N
+    odci = int(unsigned(si) >> LOG2N);
+    odcq = int(unsigned(sq) >> LOG2N);
+  };
 
-      // ---- load + convert + window -------------------------------------------------
-      if constexpr (kInt) {
-        int xi[kPts], xq[kPts];
-#pragma unroll
-        for (int q = 0; q < kPts; q++) load_raw_int<KIND, N>(buf, t + q * T, xi[q], xq[q]);
-        int dci = 0, dcq = 0;
-        if constexpr (DC) {
-          // int32 sums over the whole buffer (utility.cpp:44-48), then the unsigned
-          // division of utility.cpp:49-50: dc = int32(uint32(sum) / N), N = 2^LOG2N.
-          int si = 0, sq = 0;
-#pragma unroll
-          for (int q = 0; q < kPts; q++) { si += xi[q]; sq += xq[q]; }
-          constexpr int SEG = (T < 32) ? T : 32;
-#pragma unroll
-          for (int o = SEG / 2; o > 0; o >>= 1) {
-            si += __shfl_xor_sync(0xffffffffu, si, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          }
-          if constexpr (T > 32) {
-            if (lane == 0) { sred[2 * warp] = si; sred[2 * warp + 1] = sq; }
-            __syncthreads();
-            si = 0; sq = 0;
-            const int w0 = f * G::WARPS_PER_FFT;
-#pragma unroll
-            for (int i = 0; i < G::WARPS_PER_FFT; i++) { si += sred[2 * (w0 + i)]; sq += sred[2 * (w0 + i) + 1]; }
-          }
-          dci = static_cast<int>(static_cast<unsigned>(si) >> LOG2N);
-          dcq = static_cast<int>(static_cast<unsigned>(sq) >> LOG2N);
-        }
-        // float(int(x) - dc) * onebymax * window: onebymax is a signed power of two, so
-        // folding it into the window table is exact.
-#pragma unroll
-        for (int q = 0; q < kPts; q++) {
-          v[q].x = __fmul_rn(static_cast<float>(xi[q] - dci), w[q]);
-          v[q].y = __fmul_rn(static_cast<float>(xq[q] - dcq), w[q]);
-        }
-      } else {
-        const float2* fb = reinterpret_cast<const float2*>(buf);
-#pragma unroll
-        for (int q = 0; q < kPts; q++) v[q] = __ldg(fb + t + q * T);
-#pragma unroll
-        for (int q = 0; q < kPts; q++) {
-          v[q].x = __fmul_rn(v[q].x, w[q]);
-          v[q].y = __fmul_rn(v[q].y, w[q]);
-        }
-      }
+  Raw raw;
+  int dci = 0, dcq = 0;
+  bool live;
+  {
+    const uint8_t* buf = tile_ptr(g, 0, live);
+    if (live) raw.load(buf, t); else raw.zero();
+    if constexpr (kDC) {
+      int si, sq;
+      raw.sums(si, sq);
+      reduce_dc(si, sq, sred);
+      __syncthreads();
+      finish_dc(sred, dci, dcq);
+      tpar = 1;
+    }
+  }
 
-      // ---- FFT: Stockham passes with shared-memory exchanges ---------------------------
-      // Ping-pong tiles: a tile is rewritten only two exchanges later, and every thread has
-      // passed the intervening barrier after its last read of it, so one barrier per
-      // exchange suffices (two when there is a single tile).
-      pass_butterflies<pass_log2r(LOG2N, 0)>(v);
-#define SCN_EXCHANGE(P)                                                      \
-      {                                                                      \
-        float2* xb = (xsel & 1u) ? xch1 : xch0;                              \
-        if constexpr (G::XBUFS == 1) __syncthreads();                        \
-        pass_scatter<LOG2N, P>(v, xb, t);                                    \
-        __syncthreads();                                                     \
-        pass_gather<LOG2N>(v, xb, t);                                        \
-        xsel ^= 1u;                                                          \
-      }
-      if constexpr (NP > 1) {
-        SCN_EXCHANGE(0)
-        pass_twiddle<LOG2N, 1>(v, p.twiddles, t);
-        pass_butterflies<pass_log2r(LOG2N, 1)>(v);
-      }
-      if constexpr (NP > 2) {
-        SCN_EXCHANGE(1)
-        pass_twiddle<LOG2N, 2>(v, p.twiddles, t);
-        pass_butterflies<pass_log2r(LOG2N, 2)>(v);
-      }
-      if constexpr (NP > 3) {
-        SCN_EXCHANGE(2)
-        pass_twiddle<LOG2N, 3>(v, p.twiddles, t);
-        pass_butterflies<pass_log2r(LOG2N, 3)>(v);
-      }
+  float acc[kPts];
+  while (true) {
+    // ---- convert + window (current tile), then put the next tile's loads in flight ------------------
+    float2 v[kPts];
+    raw.convert(v, win, dci, dcq);
+    const bool cur_live = live;
+    const uint32_t cur_g = g, cur_k = k;
+    uint32_t ng = g, nk = k + 1;
+    if (nk == K) { nk = 0; ng = g + gridDim.x; }
+    const bool has_next = ng < n_groups;
+    bool next_live = false;
+    if (has_next) {
+      const uint8_t* nbuf = tile_ptr(ng, nk, next_live);
+      if (next_live) raw.load(nbuf, t); else raw.zero();
+    }
+
+    // ---- FFT: Stockham passes with shared-memory exchanges ------------------------------------------
+    // Ping-pong tiles: a tile is rewritten only two exchanges later and every thread has passed the
+    // intervening barrier after its last read of it, so one barrier per exchange suffices.
+    pass_butterflies<pass_log2r(LOG2N, 0)>(v);
+    int ndci = 0, ndcq = 0;
+#define SCN_EXCHANGE(P, LAST)                                                                   \
+    {                                                                                           \
+      float2* xb = (xsel & 1u) ? xch1 : xch0;                                                   \
+      if constexpr (G::XBUFS == 1) __syncthreads();                                             \
+      if constexpr ((P) == 0) pass0_scatter<LOG2N>(v, xb, t); else pass_scatter<LOG2N, (P)>(v, xb, t); \
+      if constexpr (kDC && (LAST)) {                                                            \
+        if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); } \
+      }                                                                                         \
+      __syncthreads();                                                                          \
+      if constexpr (kDC && (LAST)) {                                                            \
+        if (has_next) finish_dc(sred + tpar * (2 * G::RED_SLOTS), ndci, ndcq);                  \
+        tpar ^= 1u;                                                                             \
+      }                                                                                         \
+      pass_gather<LOG2N>(v, xb, t);                                                             \
+      xsel ^= 1u;                                                                               \
+    }
+    SCN_EXCHANGE(0, NP == 2)
+    pass_twiddle<LOG2N, 1>(v, p.twiddles, t);
+    dft16(v);
+    if constexpr (NP > 2) {
+      SCN_EXCHANGE(1, NP == 3)
+      pass_twiddle<LOG2N, 2>(v, p.twiddles, t);
+      dft16(v);
+    }
+    if constexpr (NP > 3) {
+      SCN_EXCHANGE(2, NP == 4)
+      pass_twiddle<LOG2N, 3>(v, p.twiddles, t);
+      dft16(v);
+    }
 #undef SCN_EXCHANGE
 
-      // ---- power, K-averaging (fp32, buffer order) -------------------------
+    // ---- power, K-averaging (fp32, buffer order) ---------------------------------------
+    float pw[kPts];
+#pragma unroll
+    for (int q = 0; q < kPts; q++) {
+      const float2 sq2 = __fmul2_rn(v[q], v[q]);            // fl(re*re), fl(im*im): no FMA contraction
+      pw[q] = __fadd_rn(sq2.x, sq2.y);
+      if constexpr (AVG) pw[q] = acc[q] = (cur_k == 0) ? pw[q] : __fadd_rn(acc[q], pw[q]);
+    }
+
+    if (cur_k == K - 1) {
+      // ---- dB + detection for spectrum s ----------------------------------------------------------------
+      const uint32_t s = cur_g * F + f;
+      uint32_t* sm = smask + spar * (F * G::WORDS);
+      float db[kPts];
+      bool anyraw = false;
 #pragma unroll
       for (int q = 0; q < kPts; q++) {
-        const float pw = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
-        acc[q] = (k == 0) ? pw : __fadd_rn(acc[q], pw);
+        const float pbar = AVG ? __fmul_rn(pw[q], p.inv_averaging) : pw[q];
+        db[q] = kDbPerLog2 * __log2f(pbar);
+        anyraw = anyraw || (db[q] > p.threshold);          // strict >, NaN never hits (process.cpp:54)
       }
-    }
-
-    // ---- dB + detection ------------------------------------------------------------------
-    float db[kPts];
-    uint32_t hitbits = 0;
+      if (p.spectra != nullptr && cur_live) {
+        float* out = p.spectra + size_t(s) * N;
 #pragma unroll
-    for (int q = 0; q < kPts; q++) {
-      const float pbar = (K == 1) ? acc[q] : __fmul_rn(acc[q], p.inv_averaging);
-      db[q] = kDbPerLog2 * __log2f(pbar);
-      hitbits |= (db[q] > p.threshold ? 1u : 0u) << q;     // strict >, NaN never hits (process.cpp:54)
-    }
-    hitbits = live ? (hitbits & candbits) : 0u;
-    if (p.spectra != nullptr && live) {
-      float* out = p.spectra + size_t(s) * N;
-#pragma unroll
-      for (int q = 0; q < kPts; q++) out[t + q * T] = db[q];
-    }
-
-    // mask words into shared memory (bit i of word i>>5)
-    if constexpr (T < 32) {
-      for (int x = tid; x < F * G::WORDS; x += G::THREADS) smask[x] = 0;
-      __syncthreads();
-    }
-#pragma unroll
-    for (int q = 0; q < kPts; q++) {
-      const uint32_t b = __ballot_sync(0xffffffffu, (hitbits >> q) & 1u);
-      const uint32_t i0 = (uint32_t(t & ~31) + q * T) ^ half;       // shifted index of lane 0's bin (T >= 32)
-      if constexpr (T >= 32) {
-        if (lane == 0) smask[f * G::WORDS + (i0 >> 5)] = b;
-      } else {
-        // two or more transforms share a warp: lanes [fl*T, fl*T+T) belong to transform f
-        const int fl = lane / T;
-        const uint32_t bits = (b >> (fl * T)) & ((1u << T) - 1u);
-        const uint32_t ib = (uint32_t(q * T)) ^ half;
-        if ((lane % T) == 0 && bits) atomicOr(&smask[f * G::WORDS + (ib >> 5)], bits << (ib & 31));
+        for (int q = 0; q < kPts; q++) out[t + q * T] = db[q];
       }
-    }
-    __syncthreads();
-
-    // per-transform scan of the mask: global mask words, exclusive prefix, hit count
-    for (int ff = warp; ff < F; ff += G::WARPS) {
-      const uint32_t ss = g * F + ff;
-      if (ss >= p.n_spectra) continue;
-      uint32_t base = 0;
-      for (int c = 0; c < G::WORDS; c += 32) {
-        const int wi = c + lane;
-        const uint32_t mw = (wi < G::WORDS) ? smask[ff * G::WORDS + wi] : 0u;
-        if (p.masks != nullptr && wi < G::WORDS) p.masks[size_t(ss) * G::WORDS + wi] = mw;
-        const uint32_t pc = __popc(mw);
-        uint32_t incl = pc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += y;
-        }
-        if (wi < G::WORDS) sprefix[ff * G::WORDS + wi] = base + incl - pc;
-        base += __shfl_sync(0xffffffffu, incl, 31);
+      // Mask words of this warp (16 words: 32 lanes x 16 bins) are owned by this warp alone.
+      // Common case: no lane of the warp has a bin above threshold -> just zero them.
+      uint32_t hitbits = 0;
+      {
+        int zf, zw;                       // (transform, word) zeroed by lane < 16
+        if constexpr (T >= 32) { zf = f; zw = int((uint32_t((t & ~31) + lane * T) ^ half) >> 5); }
+        else { zf = warp * G::FFTS_PER_WARP + lane / G::WORDS; zw = lane % G::WORDS; }
+        if (lane < 16) sm[zf * G::WORDS + zw] = 0u;
       }
-      if (lane == 0 && p.counts != nullptr) p.counts[ss] = base;
-    }
-
-    if (p.hits != nullptr) {
-      __syncthreads();
-      if (hitbits) {
+      const bool warp_any = __any_sync(0xffffffffu, anyraw);
+      uint32_t warp_bits = 0;
+      if (warp_any) {
+#pragma unroll
+        for (int q = 0; q < kPts; q++) hitbits |= (db[q] > p.threshold ? 1u : 0u) << q;
+        hitbits = cur_live ? (hitbits & candbits) : 0u;
+        warp_bits = __reduce_or_sync(0xffffffffu, hitbits);
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < kPts; q++) {
-          if ((hitbits >> q) & 1u) {
-            const uint32_t i = (uint32_t(t) + q * T) ^ half;
-            const uint32_t mw = smask[f * G::WORDS + (i >> 5)];
-            const uint32_t rank = sprefix[f * G::WORDS + (i >> 5)] + __popc(mw & ((1u << (i & 31)) - 1u));
-            if (rank < p.hit_cap) {
-              scn_hit h;
-              h.bin = i;
-              h.power_db = db[q];
-              p.hits[size_t(s) * p.hit_cap + rank] = h;
+          if ((warp_bits >> q) & 1u) {                      // warp-uniform
+            const uint32_t b = __ballot_sync(0xffffffffu, (hitbits >> q) & 1u);
+            if constexpr (T >= 32) {
+              const uint32_t i0 = (uint32_t(t & ~31) + q * T) ^ half;     // shifted index of lane 0's bin
+              if (lane == 0) sm[f * G::WORDS + (i0 >> 5)] = b;
+            } else {
+              const int fl = lane / T;
+              const uint32_t bits = (b >> (fl * T)) & ((1u << T) - 1u);
+              const uint32_t ib = uint32_t(q * T) ^ half;
+              if (t == 0 && bits) atomicOr(&sm[f * G::WORDS + (ib >> 5)], bits << (ib & 31));
             }
           }
         }
       }
+      __syncthreads();
+
+      // per-transform: global mask words + hit count (one warp per transform, round-robin)
+      for (int ff = warp; ff < F; ff += G::WARPS) {
+        const uint32_t ss = cur_g * F + ff;
+        if (ss >= p.n_spectra) continue;
+        uint32_t total = 0;
+        for (int c = 0; c < G::WORDS; c += 32) {
+          const int wi = c + lane;
+          const uint32_t mw = (wi < G::WORDS) ? sm[ff * G::WORDS + wi] : 0u;
+          if (p.masks != nullptr && wi < G::WORDS) p.masks[size_t(ss) * G::WORDS + wi] = mw;
+          total += __popc(mw);
+        }
+        total = __reduce_add_sync(0xffffffffu, total);
+        if (lane == 0 && p.counts != nullptr) p.counts[ss] = total;
+      }
+
+      // hit records, ascending in shifted bin: rank = hits in earlier words + hits in lower bits
+      if (p.hits != nullptr && warp_bits != 0u) {
+#pragma unroll
+        for (int q = 0; q < kPts; q++) {
+          if ((warp_bits >> q) & 1u) {                      // warp-uniform
+            const uint32_t i = (uint32_t(t) + q * T) ^ half;
+            const uint32_t word = i >> 5;
+            uint32_t before = 0, lower;
+            if constexpr (T >= 32) {
+              // `word` is warp-uniform and owned by this warp: its lanes count the earlier words
+              // cooperatively, and the word itself is this warp's ballot (bit == lane).
+              for (uint32_t x = lane; x < word; x += 32) before += __popc(sm[f * G::WORDS + x]);
+              before = __reduce_add_sync(0xffffffffu, before);
+              const uint32_t b = __ballot_sync(0xffffffffu, (hitbits >> q) & 1u);
+              lower = __popc(b & ((1u << lane) - 1u));
+            } else {
+              for (uint32_t x = 0; x < word; x++) before += __popc(sm[f * G::WORDS + x]);   // < 16 words
+              lower = __popc(sm[f * G::WORDS + word] & ((1u << (i & 31)) - 1u));
+            }
+            if ((hitbits >> q) & 1u) {
+              const uint32_t rank = before + lower;
+              if (rank < p.hit_cap) {
+                scn_hit h;
+                h.bin = i;
+                h.power_db = db[q];
+                p.hits[size_t(s) * p.hit_cap + rank] = h;
+              }
+            }
+          }
+        }
+      }
+      spar ^= 1u;
     }
-    __syncthreads();   // smask / sprefix / xch are reused by the next group
+
+    if (!has_next) break;
+    g = ng; k = nk; live = next_live; dci = ndci; dcq = ndcq;
   }
 }
 
