@@ -40,6 +40,10 @@ class _Config(C.Structure):
 
 
 def lib_path() -> str:
+    # SCN_LIB: developer knob to time an experiment build (tools/build_variant.sh); never a fallback
+    override = os.environ.get("SCN_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libscanner_b200.so")
 
 

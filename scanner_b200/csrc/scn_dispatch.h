@@ -43,6 +43,13 @@ inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* 
     return true;                                                                              \
   }
 
+#ifdef SCN_ONLY_LOG2N   /* experiment builds: a single transform size */
+#define SCN_VARIANT_TABLE(KIND, DC, AVG, NAME)                                                \
+  switch (log2n) {                                                                            \
+    SCN_VARIANT_CASE(SCN_ONLY_LOG2N, KIND, DC, AVG, NAME)                                     \
+    default: return false;                                                                    \
+  }
+#else
 #define SCN_VARIANT_TABLE(KIND, DC, AVG, NAME)                                                     \
   switch (log2n) {                                                                            \
     SCN_VARIANT_CASE(8, KIND, DC, AVG, NAME)                                                       \
@@ -54,5 +61,6 @@ inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* 
     SCN_VARIANT_CASE(14, KIND, DC, AVG, NAME)                                                      \
     default: return false;                                                                    \
   }
+#endif
 
 }  // namespace scn

