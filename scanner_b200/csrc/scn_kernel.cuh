@@ -29,6 +29,7 @@
 //              2: all passes' factors live in registers
 //              3: one LDG per pass + a 14-multiply product tree per tile
 //              5: six LDGs (w^1..4, w^8, w^12) + nine single products per pass (one rounding deep)
+//              6: LDG for the first twiddled pass (few distinct values per warp), mode 5 for the rest
 //              4: product tree for the LAST pass only (its 15 factors are all distinct per thread);
 //                 earlier passes (few distinct values per warp, L1 broadcast) stay LDG
 #ifndef SCN_TWMODE
@@ -339,15 +340,16 @@ spectrum_sense_kernel(const KernelParams p) {
   };
   // DC block reduction, warp part: one (si, sq) slot per warp (T >= 32) or per transform (T < 32)
   auto reduce_dc = [&](int si, int sq, int32_t* red) {
-    constexpr int SEG = (T < 32) ? T : 32;
-#pragma unroll
-    for (int o = SEG / 2; o > 0; o >>= 1) {
-      si += __shfl_xor_sync(0xffffffffu, si, o);
-      sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    }
     if constexpr (T >= 32) {
+      si = __reduce_add_sync(0xffffffffu, si);      // REDUX.SUM: one instruction per sum
+      sq = __reduce_add_sync(0xffffffffu, sq);
       if (lane == 0) { red[2 * warp] = si; red[2 * warp + 1] = sq; }
     } else {
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) {
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
       if (t == 0) { red[2 * f] = si; red[2 * f + 1] = sq; }
     }
   };
@@ -378,7 +380,8 @@ spectrum_sense_kernel(const KernelParams p) {
     else { float2 twl[15];                                                               \
            if constexpr (SCN_TWMODE == 3 || (SCN_TWMODE == 4 && (P) == NP - 1))          \
              power_twiddles<LOG2N, P>(twl, p.twiddles, t);                               \
-           else if constexpr (SCN_TWMODE == 5) product_twiddles<LOG2N, P>(twl, p.twiddles, t); \
+           else if constexpr (SCN_TWMODE == 5 || (SCN_TWMODE == 6 && (P) > 1))           \
+             product_twiddles<LOG2N, P>(twl, p.twiddles, t);                             \
            else load_twiddles<LOG2N, P>(twl, p.twiddles, t);                             \
            apply_twiddles(v, twl); }
 
