@@ -375,15 +375,18 @@ spectrum_sense_kernel(const KernelParams p) {
   if constexpr (kHoist1) load_twiddles<LOG2N, 1>(twr1, p.twiddles, t);
   if constexpr (kHoist2 && NP > 2) load_twiddles<LOG2N, 2>(twr2, p.twiddles, t);
   if constexpr (kHoist3 && NP > 3) load_twiddles<LOG2N, 3>(twr3, p.twiddles, t);
-#define SCN_TWIDDLE(P, HOISTED, REGS)                                                    \
-    if constexpr (HOISTED) { apply_twiddles(v, REGS); }                                  \
-    else { float2 twl[15];                                                               \
-           if constexpr (SCN_TWMODE == 3 || (SCN_TWMODE == 4 && (P) == NP - 1))          \
-             power_twiddles<LOG2N, P>(twl, p.twiddles, t);                               \
-           else if constexpr (SCN_TWMODE == 5 || (SCN_TWMODE == 6 && (P) > 1))           \
-             product_twiddles<LOG2N, P>(twl, p.twiddles, t);                             \
-           else load_twiddles<LOG2N, P>(twl, p.twiddles, t);                             \
-           apply_twiddles(v, twl); }
+// The twiddles of pass P do not depend on the exchange that feeds it, so they are produced BEFORE
+// the scatter/barrier (their loads and products overlap the barrier wait) and applied after the gather.
+#define SCN_TWIDDLE_PREP(P, HOISTED, TWL)                                                \
+    if constexpr (!(HOISTED)) {                                                          \
+      if constexpr (SCN_TWMODE == 3 || (SCN_TWMODE == 4 && (P) == NP - 1))               \
+        power_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                    \
+      else if constexpr (SCN_TWMODE == 5 || (SCN_TWMODE == 6 && (P) > 1))                \
+        product_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
+      else load_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
+    }
+#define SCN_TWIDDLE_APPLY(HOISTED, REGS, TWL)                                            \
+    if constexpr (HOISTED) { apply_twiddles(v, REGS); } else { apply_twiddles(v, TWL); }
 
   Raw raw;
   int dci = 0, dcq = 0;
@@ -444,17 +447,25 @@ spectrum_sense_kernel(const KernelParams p) {
       pass_gather<LOG2N>(v, xb, t);                                                             \
       xsel ^= 1u;                                                                               \
     }
-    SCN_EXCHANGE(0, NP == 2)
-    SCN_TWIDDLE(1, kHoist1, twr1)
-    dft16(v);
+    {
+      float2 twl[15];
+      SCN_TWIDDLE_PREP(1, kHoist1, twl)
+      SCN_EXCHANGE(0, NP == 2)
+      SCN_TWIDDLE_APPLY(kHoist1, twr1, twl)
+      dft16(v);
+    }
     if constexpr (NP > 2) {
+      float2 twl[15];
+      SCN_TWIDDLE_PREP(2, kHoist2, twl)
       SCN_EXCHANGE(1, NP == 3)
-      SCN_TWIDDLE(2, kHoist2, twr2)
+      SCN_TWIDDLE_APPLY(kHoist2, twr2, twl)
       dft16(v);
     }
     if constexpr (NP > 3) {
+      float2 twl[15];
+      SCN_TWIDDLE_PREP(3, kHoist3, twl)
       SCN_EXCHANGE(2, NP == 4)
-      SCN_TWIDDLE(3, kHoist3, twr3)
+      SCN_TWIDDLE_APPLY(kHoist3, twr3, twl)
       dft16(v);
     }
 #undef SCN_EXCHANGE
@@ -578,7 +589,8 @@ spectrum_sense_kernel(const KernelParams p) {
     if (!has_next) break;
     g = ng; k = nk; live = next_live; dci = ndci; dcq = ndcq;
   }
-#undef SCN_TWIDDLE
+#undef SCN_TWIDDLE_PREP
+#undef SCN_TWIDDLE_APPLY
 }
 
 }  // namespace scn
