@@ -94,7 +94,7 @@ typedef struct scn_hit {
 
 typedef struct scn_config {
   int32_t device;               /* CUDA ordinal */
-  uint32_t sample_count;        /* N: FFT size == samples per buffer (process.cpp:78); power of two, 256..16384 */
+  uint32_t sample_count;        /* N: FFT size == samples per buffer (process.cpp:78); power of two, 256..65536 (above 16384: four-step path through an HBM intermediate) */
   uint32_t sample_rate;         /* Hz (process.cpp:79) */
   uint32_t enob;                /* effective number of bits (scan.cpp:138,183,196) */
   uint32_t sample_kind;         /* SCN_KIND_* */

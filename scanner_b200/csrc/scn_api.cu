@@ -22,6 +22,16 @@ cudaError_t launch_summarize(const uint32_t* masks, const uint32_t* counts, uint
                              uint32_t* records, int num_sms, cudaStream_t stream);
 cudaError_t launch_merge(const uint32_t* parts, uint32_t n_parts, uint32_t n_steps, uint32_t rec_words,
                          uint32_t* out, cudaStream_t stream);
+// scn_large.cu: four-step path for N = 2^15, 2^16
+cudaError_t launch_dc_sums(uint32_t kind, const uint8_t* raw, uint32_t n_buffers, uint32_t n, int2* dcs,
+                           int num_sms, cudaStream_t stream);
+cudaError_t launch_columns(uint32_t kind, const uint8_t* raw, uint32_t n_buffers, uint32_t n2_count,
+                           const float* window, const float2* wn, const int2* dcs, float2* y, int num_sms,
+                           cudaStream_t stream);
+cudaError_t launch_finalize(const float* power, uint32_t n_spectra, uint32_t n2_count, float threshold,
+                            uint32_t use_window, uint32_t dc_ignore, float* spectra, uint32_t* masks,
+                            uint32_t* counts, scn_hit* hits, uint32_t hit_cap, int num_sms, cudaStream_t stream);
+constexpr int kMaxLog2NLarge = 16;   // sizes above kMaxLog2N go through the four-step path
 }  // namespace scn
 
 namespace {
@@ -89,11 +99,20 @@ struct scn_ctx {
   uint32_t hit_cap = 0;
   float onebymax = 1.0f;
   float* d_window = nullptr;
+  float* d_ones = nullptr;       // unit window for the row transforms of the four-step path
   float2* d_twiddles = nullptr;
   scn::KernelVariant variant{};
   int ctas_per_sm = 1;
   int num_sms = 1;
   int regs = 0;
+  // four-step path (N = 2^15, 2^16): N = 16 x N2
+  bool large = false;
+  int log2n2 = 0;
+  float2* d_wn = nullptr;        // exp(-2 pi i m / N), m < N
+  float2* d_y = nullptr;         // intermediate [chunk buffers][16][N2]
+  float* d_p = nullptr;          // power [chunk spectra][16][N2]
+  int2* d_dcs = nullptr;         // per-buffer dc
+  uint32_t chunk_spectra = 0;
   std::vector<Slot> slots;
   uint32_t next_slot = 0;
   uint64_t launches = 0;
@@ -126,8 +145,58 @@ std::vector<float2> build_twiddles(int log2n) {
   return tw;
 }
 
+int launch_rows(scn_ctx* c, const void* d_y, uint32_t n_rows, float* d_power, cudaStream_t stream);
+
+// N = 2^15 / 2^16: dc sums -> columns -> row FFTs (fused kernel in row mode) -> finalize, chunked so the
+// intermediate stays within the context's scratch.
+int launch_large(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d_spectra, uint32_t* d_masks,
+                 uint32_t* d_counts, scn_hit* d_hits, cudaStream_t stream) {
+  const uint32_t N = c->cfg.sample_count, N2 = N / 16, K = c->K;
+  const bool dc = c->cfg.correct_dc_offset && c->cfg.sample_kind != SCN_KIND_FLOAT_COMPLEX;
+  // scratch grows on demand up to the chunk cap (intermediate <= 256 MiB)
+  {
+    uint64_t cap = (256ull << 20) / (uint64_t(K) * N * sizeof(float2));
+    if (cap < 1) cap = 1;
+    const uint32_t want = n_spectra < cap ? n_spectra : uint32_t(cap);
+    if (want > c->chunk_spectra) {
+      SCN_CUDA(cudaStreamSynchronize(stream));
+      if (c->d_y) cudaFree(c->d_y);
+      if (c->d_p) cudaFree(c->d_p);
+      if (c->d_dcs) cudaFree(c->d_dcs);
+      c->d_y = nullptr; c->d_p = nullptr; c->d_dcs = nullptr; c->chunk_spectra = 0;
+      SCN_CUDA(cudaMalloc(&c->d_y, sizeof(float2) * size_t(want) * K * N));
+      SCN_CUDA(cudaMalloc(&c->d_p, sizeof(float) * size_t(want) * N));
+      SCN_CUDA(cudaMalloc(&c->d_dcs, sizeof(int2) * size_t(want) * K));
+      c->chunk_spectra = want;
+    }
+  }
+  for (uint32_t first = 0; first < n_spectra; first += c->chunk_spectra) {
+    const uint32_t ns = (n_spectra - first < c->chunk_spectra) ? (n_spectra - first) : c->chunk_spectra;
+    const uint32_t nb = ns * K;
+    const uint8_t* raw = static_cast<const uint8_t*>(d_raw) + size_t(first) * K * c->buf_bytes;
+    if (dc) {
+      SCN_CUDA(scn::launch_dc_sums(c->cfg.sample_kind, raw, nb, N, c->d_dcs, c->num_sms, stream));
+      c->launches++;
+    }
+    SCN_CUDA(scn::launch_columns(c->cfg.sample_kind, raw, nb, N2, c->d_window, c->d_wn, dc ? c->d_dcs : nullptr,
+                                 c->d_y, c->num_sms, stream));
+    c->launches++;
+    int rc = launch_rows(c, c->d_y, ns * 16, c->d_p, stream);
+    if (rc != SCN_OK) return rc;
+    SCN_CUDA(scn::launch_finalize(c->d_p, ns, N2, c->cfg.threshold, c->cfg.use_window, c->cfg.dc_ignore_window,
+                                  d_spectra ? d_spectra + size_t(first) * N : nullptr,
+                                  d_masks ? d_masks + size_t(first) * c->words : nullptr,
+                                  d_counts ? d_counts + first : nullptr,
+                                  d_hits ? d_hits + size_t(first) * c->hit_cap : nullptr, c->hit_cap, c->num_sms,
+                                  stream));
+    c->launches++;
+  }
+  return SCN_OK;
+}
+
 int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d_spectra,
                      uint32_t* d_masks, uint32_t* d_counts, scn_hit* d_hits, cudaStream_t stream) {
+  if (c->large) return launch_large(c, d_raw, n_spectra, d_spectra, d_masks, d_counts, d_hits, stream);
   scn::KernelParams p{};
   p.raw = static_cast<const uint8_t*>(d_raw);
   p.window = c->d_window;
@@ -145,6 +214,30 @@ int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d
   p.dc_ignore = c->cfg.dc_ignore_window;
   const uint32_t F = uint32_t(c->variant.transforms_per_cta);
   const uint32_t n_groups = (n_spectra + F - 1) / F;
+  uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
+  if (grid > n_groups) grid = n_groups;
+  if (grid == 0) return SCN_OK;
+  void* args[] = {&p};
+  SCN_CUDA(cudaLaunchKernel(c->variant.func, dim3(grid), dim3(c->variant.threads), args,
+                            c->variant.smem_bytes, stream));
+  c->launches++;
+  return SCN_OK;
+}
+
+// Row mode of the fused kernel: n_rows independent N2-point transforms of fp32 complex rows, 16 rows per
+// intermediate buffer, K-averaged power out.
+int launch_rows(scn_ctx* c, const void* d_y, uint32_t n_rows, float* d_power, cudaStream_t stream) {
+  scn::KernelParams p{};
+  p.raw = static_cast<const uint8_t*>(d_y);
+  p.window = c->d_ones;
+  p.twiddles = c->d_twiddles;
+  p.n_spectra = n_rows;
+  p.averaging = c->K;
+  p.inv_averaging = 1.0f / float(c->K);
+  p.rpb_shift = 4;
+  p.power_out = d_power;
+  const uint32_t F = uint32_t(c->variant.transforms_per_cta);
+  const uint32_t n_groups = (n_rows + F - 1) / F;
   uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
   if (grid > n_groups) grid = n_groups;
   if (grid == 0) return SCN_OK;
@@ -254,9 +347,9 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
   const bool td = mode == SCN_MODE_TIME_DOMAIN;
   if (bytes_per_sample(cf.sample_kind) == 0)
     return fail(SCN_ERR_INVALID, "sample_kind %u is not a SampleKind", cf.sample_kind);
-  if (!td && (log2n < scn::kMinLog2N || log2n > scn::kMaxLog2N))
+  if (!td && (log2n < scn::kMinLog2N || log2n > scn::kMaxLog2NLarge))
     return fail(SCN_ERR_INVALID, "sample_count %u unsupported: power of two in [%d, %d] required",
-                cf.sample_count, 1 << scn::kMinLog2N, 1 << scn::kMaxLog2N);
+                cf.sample_count, 1 << scn::kMinLog2N, 1 << scn::kMaxLog2NLarge);
   if (td && (cf.sample_count == 0 || cf.sample_count % 8 != 0))
     return fail(SCN_ERR_INVALID, "sample_count %u must be a positive multiple of 8", cf.sample_count);
   if (cf.sample_kind != SCN_KIND_FLOAT_COMPLEX) {
@@ -305,7 +398,12 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
   auto bail = [&](int code) { scn_destroy(c); return code; };
 
   if (!td) {
-    if (!scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant))
+    c->large = log2n > scn::kMaxLog2N;
+    c->log2n2 = c->large ? log2n - 4 : log2n;
+    const bool found = c->large
+        ? scn::find_variant(SCN_KIND_FLOAT_COMPLEX, c->log2n2, false, K > 1, &c->variant)
+        : scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant);
+    if (!found)
       return bail(fail(SCN_ERR_INVALID, "no kernel variant for kind %u, N %u", cf.sample_kind, cf.sample_count));
     e = cudaFuncSetAttribute(c->variant.func, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(c->variant.smem_bytes));
@@ -328,10 +426,24 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     e = cudaMalloc(&c->d_window, sizeof(float) * cf.sample_count);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_window, w.data(), sizeof(float) * cf.sample_count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(e)));
-    std::vector<float2> tw = build_twiddles(log2n);
+    std::vector<float2> tw = build_twiddles(c->log2n2);
     e = cudaMalloc(&c->d_twiddles, sizeof(float2) * tw.size());
     if (e == cudaSuccess) e = cudaMemcpy(c->d_twiddles, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "twiddle upload failed: %s", cudaGetErrorString(e)));
+    if (c->large) {
+      const uint32_t N = cf.sample_count, N2 = N / 16;
+      std::vector<float> ones(N2, 1.0f);
+      std::vector<float2> wn(N);
+      for (uint32_t m = 0; m < N; m++) {
+        const double a = -2.0 * kPi * double(m) / double(N);
+        wn[m] = make_float2(float(std::cos(a)), float(std::sin(a)));
+      }
+      e = cudaMalloc(&c->d_ones, sizeof(float) * N2);
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_ones, ones.data(), sizeof(float) * N2, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc(&c->d_wn, sizeof(float2) * N);
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_wn, wn.data(), sizeof(float2) * N, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "four-step scratch allocation failed: %s", cudaGetErrorString(e)));
+    }
   } else {
     c->variant.name = "time_domain_threshold";
     c->variant.threads = 256;
@@ -350,6 +462,11 @@ SCN_API int scn_destroy(scn_ctx* c) {
   }
   if (c->d_window) cudaFree(c->d_window);
   if (c->d_twiddles) cudaFree(c->d_twiddles);
+  if (c->d_ones) cudaFree(c->d_ones);
+  if (c->d_wn) cudaFree(c->d_wn);
+  if (c->d_y) cudaFree(c->d_y);
+  if (c->d_p) cudaFree(c->d_p);
+  if (c->d_dcs) cudaFree(c->d_dcs);
   delete c;
   return SCN_OK;
 }

@@ -60,6 +60,11 @@ struct KernelParams {
   float threshold;
   uint32_t use_window;
   uint32_t dc_ignore;
+  // Row mode (second step of the four-step path for N > 2^14, scn_large.cu): the "spectra" are the
+  // 2^rpb_shift rows of each intermediate buffer and the kernel stops after |X|^2 / averaging,
+  // writing fp32 power [row][N] to power_out.  rpb_shift == 0 and power_out == nullptr otherwise.
+  uint32_t rpb_shift;
+  float* __restrict__ power_out;
 };
 
 // dB = 10*log2(sqrt(p))/log2(10) = (5/log2(10)) * log2(p)
@@ -336,7 +341,11 @@ spectrum_sense_kernel(const KernelParams p) {
   auto tile_ptr = [&](uint32_t gg, uint32_t kk, bool& live) -> const uint8_t* {
     const uint32_t s = gg * F + f;
     live = s < p.n_spectra;
-    return p.raw + (size_t(live ? s : 0) * K + kk) * kBufBytes;
+    const uint32_t ss = live ? s : 0;
+    // buffer (ss >> rpb_shift) * K + kk, row (ss & mask) inside it; rpb_shift == 0: buffer ss*K + kk
+    const size_t buffer = size_t(ss >> p.rpb_shift) * K + kk;
+    const size_t row = (buffer << p.rpb_shift) + (ss & ((1u << p.rpb_shift) - 1u));
+    return p.raw + row * kBufBytes;
   };
   // DC block reduction, warp part: one (si, sq) slot per warp (T >= 32) or per transform (T < 32)
   auto reduce_dc = [&](int si, int sq, int32_t* red) {
@@ -479,7 +488,15 @@ spectrum_sense_kernel(const KernelParams p) {
       if constexpr (AVG) pw[q] = acc[q] = (cur_k == 0) ? pw[q] : __fadd_rn(acc[q], pw[q]);
     }
 
-    if (epilogue_tile) {
+    if (epilogue_tile && p.power_out != nullptr) {
+      // ---- row mode: averaged power out, detection happens in the finalize kernel -----------------------
+      const uint32_t s = cur_g * F + f;
+      if (cur_live) {
+        float* out = p.power_out + size_t(s) * N;
+#pragma unroll
+        for (int q = 0; q < kPts; q++) out[t + q * T] = AVG ? __fmul_rn(pw[q], p.inv_averaging) : pw[q];
+      }
+    } else if (epilogue_tile) {
       // ---- dB + detection for spectrum s ----------------------------------------------------------------
       const uint32_t s = cur_g * F + f;
       uint32_t* sm = smask + spar * (F * G::WORDS);

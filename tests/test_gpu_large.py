@@ -1,0 +1,44 @@
+"""GPU: N = 2^15 and 2^16 (four-step path through an HBM intermediate, scn_large.cu) against the oracle:
+same contract as the in-CTA sizes -- masks / counts / hit order bit-exact, power within 1e-3 dB."""
+import numpy as np
+import pytest
+
+import scanner_b200 as S
+from tests.test_gpu_parity import run_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("log2n", [15, 16])
+@pytest.mark.parametrize("kind,enob,dc", [(S.KIND_BYTE_COMPLEX, 8, True), (S.KIND_SHORT_COMPLEX, 12, False),
+                                          (S.KIND_SHORT, 12, True), (S.KIND_FLOAT_COMPLEX, 0, False)])
+def test_large_parity(log2n, kind, enob, dc):
+    # one more twiddle stage (W_N in fp32) than the in-CTA path: rms error class 4x the CPU fp32 FFT
+    run_case(kind, 1 << log2n, enob, dc, 1, 3, seed=700 + log2n * 10 + kind, acc_factor=4.0)
+
+
+def test_large_averaging_and_chunking():
+    # K = 4 averaging; 5 spectra through a context sized for 2 (chunked submits), small record cap
+    run_case(S.KIND_SHORT_COMPLEX, 1 << 15, 12, True, 4, 5, seed=801, max_spectra=2, hit_cap=7, acc_factor=4.0)
+
+
+def test_large_band_edges():
+    n = 1 << 16
+    rect = S.window_build(S.WIN_RECTANGULAR, n)
+    use_w, half = S.use_window(0.75, n), n // 2
+    idx = [half - use_w - 1, half - use_w, half + use_w, half + use_w + 1, half - 4, half - 3, half + 3, half + 4, 5, n - 7]
+    t = np.arange(n)
+    x = np.zeros((len(idx), n, 2), np.float32)
+    for s, i in enumerate(idx):
+        j = (i + half) % n
+        x[s, :, 0] = np.cos(2 * np.pi * ((j * t) % n) / n)
+        x[s, :, 1] = np.sin(2 * np.pi * ((j * t) % n) / n)
+    with S.SpectrumSense(n, 8_000_000, 0, 20.0, rect, sample_kind=S.KIND_FLOAT_COMPLEX, max_spectra=len(idx)) as ss:
+        res = ss.process(x)
+    for s, i in enumerate(idx):
+        j = (i + half) % n
+        want = int((half - use_w) <= i <= (half + use_w) and not (j < 4 or (n - j) < 4))
+        assert res["hit_count"][s] == want, (i, res["hit_count"][s])
+        if want:
+            assert res["hits"]["bin"][s, 0] == i and abs(res["hits"]["power_db"][s, 0] - 10 * np.log10(n)) < 1e-3
+            assert res["hit_mask"][s, i >> 5] == np.uint32(1 << (i & 31))

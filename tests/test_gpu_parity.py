@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DB_TOL = 1e-3   # dB, stated by north_star
 
 
-def check_power(got_db, true_db64, ref32_db=None):
+def check_power(got_db, true_db64, ref32_db=None, acc_factor=2.5):
     """Power parity.  An fp32 FFT -- FFTW included -- has an ABSOLUTE error of a few
     1e-7 of the spectrum's rms, so a deep null (a noise bin that happens to land 40 dB under the
     floor) has an unbounded dB error.  The 1e-3 dB bar is therefore asserted on every bin within
@@ -34,14 +34,14 @@ def check_power(got_db, true_db64, ref32_db=None):
     lin = (np.abs(mag_got - mag_true) / rms)[weak]
     if lin.size:
         assert lin.max() < 2.3e-5, f"max linear error {lin.max()} of rms on bins below the floor"
-    if ref32_db is not None:   # FFT accuracy class: rms error no worse than 2.5x the CPU fp32 restatement
+    if ref32_db is not None:   # FFT accuracy class: rms error no worse than acc_factor (2.5) x the CPU fp32 restatement
         lin_all = np.abs(mag_got - mag_true) / rms
         lin32 = np.abs(10.0 ** (ref32_db.astype(np.float64) / 10.0) - mag_true) / rms
-        assert np.sqrt(np.mean(lin_all ** 2)) < 2.5 * np.sqrt(np.mean(lin32 ** 2)) + 1e-8
+        assert np.sqrt(np.mean(lin_all ** 2)) < acc_factor * np.sqrt(np.mean(lin32 ** 2)) + 1e-8
 
 
 def run_case(kind, n, enob, dc, K, n_spectra, seed, win_type=S.WIN_BLACKMAN_HARRIS, max_spectra=None,
-             hit_cap=0):
+             hit_cap=0, acc_factor=2.5):
     raw = synth.make_buffers(kind, n, n_spectra * K, enob, seed)
     window = S.window_build(win_type, n)
     use_w = S.use_window(0.75, n)
@@ -59,7 +59,7 @@ def run_case(kind, n, enob, dc, K, n_spectra, seed, win_type=S.WIN_BLACKMAN_HARR
     np.testing.assert_array_equal(got["hit_mask"], ref32["hit_mask"])
     np.testing.assert_array_equal(got["hit_count"], truth["hit_count"])
     assert truth["hit_count"].sum() > 0
-    check_power(got["spectra_db"], truth["spectra_db64"], ref32["spectra_db"])
+    check_power(got["spectra_db"], truth["spectra_db64"], ref32["spectra_db"], acc_factor)
     # hit records: ascending bins, same set as the mask, same dB as the spectrum
     cap = got["hits"].shape[1]
     for s in range(n_spectra):
