@@ -407,8 +407,18 @@ def main() -> None:
     bps = algorithmic_bytes_per_sample(wl, spectrum)
     achieved = samples_per_rank * bps / (kern_ms * 1e-3) / 1e9
     info = ctx.kernel_info()
+    # DRAM bytes per launch from the committed ncu --set full capture of this workload (profiles/), if any
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and spectrum:
+        with open(tpath) as f:
+            tj = json.load(f).get(args.workload)
+        if tj and tj["samples_per_launch"] == samples_per_rank:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": ctx.kernel_name, "kernel_ms": kern_ms,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": samples_per_rank * bps,
+                "kernel": ctx.kernel_name, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_sample": bps, "peak_source": peak_src,
                 "kernel_msamples_per_s": samples_per_rank / (kern_ms * 1e-3) / 1e6, "occupancy": info}
 

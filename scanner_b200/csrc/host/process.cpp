@@ -93,71 +93,108 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   scn_ctx* ctx = CreateContext(q->m_kind, q->GetEnob(), q->GetCorrectDCOffset(), maxSpectra);
   const size_t bufBytes = q->GetBufferBytes();
   const uint32_t N = m_sampleCount;
-  void* staging = nullptr;                              // contiguous pinned batch
-  if (scn_alloc_pinned(bufBytes * size_t(maxSpectra) * K, &staging) != SCN_OK) Die("scn_alloc_pinned");
+
+  // Two batches in flight: while batch i is on the GPU (H2D -> fused kernel -> D2H on its ticket's
+  // stream), batch i+1 is drained from the queue and staged.  Results are never held back waiting for
+  // more input: with nothing queued the in-flight batch is collected at once.
+  struct InFlight {
+    void* staging = nullptr;                       // contiguous pinned batch
+    std::vector<SampleQueue::MessageType*> batch;
+    uint32_t ticket = 0, nSpectra = 0;
+    bool active = false;
+  } slot[2];
+  for (auto& s : slot)
+    if (scn_alloc_pinned(bufBytes * size_t(maxSpectra) * K, &s.staging) != SCN_OK) Die("scn_alloc_pinned");
   std::vector<uint32_t> counts(maxSpectra);
   std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * N : 0);
   std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
-  std::vector<SampleQueue::MessageType*> batch;
 
-  while (uint32_t n = q->GetNextBatch(batch, maxSpectra * K, K)) {
-    uint32_t nSpectra = n / K;
-    if (nSpectra == 0) {                                // trailing partial group at end of stream: dropped
-      for (auto* m : batch) q->MessageProcessed(m);
-      continue;
+  auto finish = [&](InFlight& f) {
+    const uint32_t nSpectra = f.nSpectra;
+    if (nSpectra) {
+      if (scn_collect(ctx, f.ticket, nullptr, nullptr, counts.data(), hits.empty() ? nullptr : hits.data(),
+                      tdmm.empty() ? nullptr : tdmm.data()) != SCN_OK)
+        Die("scn_collect");
+      std::lock_guard<std::mutex> lock(g_printMutex);
+      for (uint32_t s = 0; s < nSpectra; s++) {
+        // the first message of the group carries the spectrum's identity
+        SampleQueue::MessageHeader& header = f.batch[size_t(s) * K]->GetHeader();
+        for (uint32_t k = 0; k < K; k++) {
+          SampleQueue::MessageHeader& h = f.batch[size_t(s) * K + k]->GetHeader();
+          if (h.m_time != 0 && m_out) {                   // process.cpp:280-287
+            char tbuf[64];
+            TimeToString(h.m_time, tbuf, sizeof(tbuf));
+            fprintf(m_out, "Start scan at %s\n", tbuf);
+            fflush(m_out);
+          }
+        }
+        bool doWrite = false;
+        if (m_mode == TimeDomain) {
+          doWrite = counts[s] != 0;                       // process.cpp:226-235
+          if (doWrite && m_out) {
+            fprintf(m_out, "Sequence[%llu]: ", (unsigned long long)header.m_sequenceId);
+            fprintf(m_out, "Max signal %f above threshold %f frequency %.0f, min %f\n", tdmm[2 * s],
+                    m_threshold, header.m_frequency, tdmm[2 * s + 1]);
+          }
+        } else {
+          const uint32_t c = counts[s];
+          for (uint32_t r = 0; r < c && r < N; r++) {
+            const scn_hit& h = hits[size_t(s) * N + r];
+            const uint64_t hz = scn_hit_frequency(header.m_frequency, m_sampleRate, N, h.bin);
+            if (m_out) fprintf(m_out, "freq %lu power_db %f\n", (unsigned long)hz, h.power_db);   // process.cpp:57
+            if (m_sink) m_sink(Detection{header.m_sequenceId, header.m_frequency, hz, h.power_db, h.bin});
+          }
+          m_hitCount += c;
+          doWrite = c > 1047;                             // process.cpp:62
+        }
+        if (doWrite) {
+          if (m_out) fflush(m_out);
+        } else {
+          q->SendAck();                                   // process.cpp:303-307
+        }
+        ProcessWrite(doWrite, header.m_frequency, header.m_sequenceId);
+      }
     }
-    for (uint32_t i = 0; i < nSpectra * K; i++)
-      memcpy(static_cast<char*>(staging) + size_t(i) * bufBytes, batch[i]->GetData(), bufBytes);
-    uint32_t ticket = 0;
-    if (scn_submit(ctx, staging, nSpectra, &ticket) != SCN_OK) Die("scn_submit");
-    if (scn_collect(ctx, ticket, nullptr, nullptr, counts.data(), hits.empty() ? nullptr : hits.data(),
-                    tdmm.empty() ? nullptr : tdmm.data()) != SCN_OK)
-      Die("scn_collect");
-    m_launches++;
+    for (auto* m : f.batch) q->MessageProcessed(m);       // process.cpp:309
+    m_buffersProcessed += f.batch.size();
+    f.batch.clear();
+    f.active = false;
+  };
 
-    std::lock_guard<std::mutex> lock(g_printMutex);
-    for (uint32_t s = 0; s < nSpectra; s++) {
-      // the first message of the group carries the spectrum's identity
-      SampleQueue::MessageHeader& header = batch[size_t(s) * K]->GetHeader();
-      for (uint32_t k = 0; k < K; k++) {
-        SampleQueue::MessageHeader& h = batch[size_t(s) * K + k]->GetHeader();
-        if (h.m_time != 0 && m_out) {                   // process.cpp:280-287
-          char tbuf[64];
-          TimeToString(h.m_time, tbuf, sizeof(tbuf));
-          fprintf(m_out, "Start scan at %s\n", tbuf);
-          fflush(m_out);
-        }
+  uint32_t cur = 0;
+  while (true) {
+    InFlight& next = slot[cur];
+    InFlight& prev = slot[cur ^ 1];
+    const uint32_t n = q->GetNextBatch(next.batch, maxSpectra * K, K, /*wait=*/!prev.active);
+    if (n) {
+      next.nSpectra = n / K;                              // a trailing partial group at end of stream is dropped
+      for (uint32_t i = 0; i < next.nSpectra * K; i++)
+        memcpy(static_cast<char*>(next.staging) + size_t(i) * bufBytes, next.batch[i]->GetData(), bufBytes);
+      if (next.nSpectra) {
+        if (scn_submit(ctx, next.staging, next.nSpectra, &next.ticket) != SCN_OK) Die("scn_submit");
+        m_launches++;
       }
-      bool doWrite = false;
-      if (m_mode == TimeDomain) {
-        doWrite = counts[s] != 0;                       // process.cpp:226-235
-        if (doWrite && m_out) {
-          fprintf(m_out, "Sequence[%llu]: ", (unsigned long long)header.m_sequenceId);
-          fprintf(m_out, "Max signal %f above threshold %f frequency %.0f, min %f\n", tdmm[2 * s],
-                  m_threshold, header.m_frequency, tdmm[2 * s + 1]);
-        }
-      } else {
-        const uint32_t c = counts[s];
-        for (uint32_t r = 0; r < c && r < N; r++) {
-          const scn_hit& h = hits[size_t(s) * N + r];
-          const uint64_t hz = scn_hit_frequency(header.m_frequency, m_sampleRate, N, h.bin);
-          if (m_out) fprintf(m_out, "freq %lu power_db %f\n", (unsigned long)hz, h.power_db);   // process.cpp:57
-          if (m_sink) m_sink(Detection{header.m_sequenceId, header.m_frequency, hz, h.power_db, h.bin});
-        }
-        m_hitCount += c;
-        doWrite = c > 1047;                             // process.cpp:62
-      }
-      if (doWrite) {
-        if (m_out) fflush(m_out);
-      } else {
-        q->SendAck();                                   // process.cpp:303-307
-      }
-      ProcessWrite(doWrite, header.m_frequency, header.m_sequenceId);
+      next.active = true;
     }
-    for (auto* m : batch) q->MessageProcessed(m);       // process.cpp:309
-    m_buffersProcessed += n;
+    if (prev.active) finish(prev);
+    if (n) cur ^= 1;
+    else if (!slot[0].active && !slot[1].active) {
+      // nothing in flight and the non-blocking poll found nothing: block, or stop when drained
+      const uint32_t m = q->GetNextBatch(slot[cur].batch, maxSpectra * K, K, /*wait=*/true);
+      if (m == 0) break;
+      InFlight& f = slot[cur];
+      f.nSpectra = m / K;
+      for (uint32_t i = 0; i < f.nSpectra * K; i++)
+        memcpy(static_cast<char*>(f.staging) + size_t(i) * bufBytes, f.batch[i]->GetData(), bufBytes);
+      if (f.nSpectra) {
+        if (scn_submit(ctx, f.staging, f.nSpectra, &f.ticket) != SCN_OK) Die("scn_submit");
+        m_launches++;
+      }
+      f.active = true;
+      cur ^= 1;
+    }
   }
-  scn_free_pinned(staging);
+  for (auto& s : slot) scn_free_pinned(s.staging);
   scn_destroy(ctx);
 }
 

@@ -119,12 +119,14 @@ SampleQueue::MessageType* SampleQueue::GetNextSamples() {
   return message;
 }
 
-uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple) {
+uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple,
+                                   bool wait) {
   out.clear();
   if (multiple == 0) multiple = 1;
   std::unique_lock<std::mutex> lock(m_mutex);
   // a group of `multiple` buffers forms one averaged spectrum: wait for a whole group (or the end)
-  m_conditionEmpty.wait(lock, [&] { return m_done || m_buffer.size() >= multiple; });
+  if (wait) m_conditionEmpty.wait(lock, [&] { return m_done || m_buffer.size() >= multiple; });
+  else if (!(m_done || m_buffer.size() >= multiple)) return 0;
   size_t take = m_buffer.size() < maxCount ? m_buffer.size() : maxCount;
   if (!(m_done && m_buffer.size() <= maxCount)) take -= take % multiple;
   if (take == 0) return 0;

@@ -66,7 +66,10 @@ class SampleQueue {
   MessageType* GetNextSamples();                                   // nullptr == done and drained
   // Blocks for the first message, then takes what is queued: up to maxCount, a multiple of `multiple`
   // unless the queue is done.  Returns the number taken (0 == done and drained).
-  uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1);
+  // wait == false: never blocks -- returns 0 when no whole group is queued yet (used by the consumer to
+  // finish an in-flight batch instead of sleeping on the queue).
+  uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1,
+                        bool wait = true);
   void MessageProcessed(MessageType* message);
 
   void BeginWrite(uint64_t startSequenceId, std::string fileName);

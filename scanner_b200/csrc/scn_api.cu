@@ -401,7 +401,7 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     c->large = log2n > scn::kMaxLog2N;
     c->log2n2 = c->large ? log2n - 4 : log2n;
     const bool found = c->large
-        ? scn::find_variant(SCN_KIND_FLOAT_COMPLEX, c->log2n2, false, K > 1, &c->variant)
+        ? scn::variant_float_rows(c->log2n2, K > 1, &c->variant)
         : scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant);
     if (!found)
       return bail(fail(SCN_ERR_INVALID, "no kernel variant for kind %u, N %u", cf.sample_kind, cf.sample_count));

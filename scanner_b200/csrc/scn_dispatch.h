@@ -21,6 +21,8 @@ bool variant_byte_complex(int log2n, bool dc, bool avg, KernelVariant* out);
 bool variant_short(int log2n, bool dc, bool avg, KernelVariant* out);
 bool variant_short_complex(int log2n, bool dc, bool avg, KernelVariant* out);
 bool variant_float_complex(int log2n, bool dc, bool avg, KernelVariant* out);
+// row mode of the four-step path: fp32 complex rows of 2^11 / 2^12 points, power out
+bool variant_float_rows(int log2n, bool avg, KernelVariant* out);
 
 // avg: K > 1 (keeps the 16 accumulators live across the K loop; K == 1 kernels do not pay for them)
 inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* out) {

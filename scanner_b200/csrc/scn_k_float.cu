@@ -5,4 +5,28 @@ bool variant_float_complex(int log2n, bool /*dc*/, bool avg, KernelVariant* out)
   if (avg) { SCN_VARIANT_TABLE(SCN_KIND_FLOAT_COMPLEX, false, true, "spectrum_sense<fp32 IQ, avg>") }
   SCN_VARIANT_TABLE(SCN_KIND_FLOAT_COMPLEX, false, false, "spectrum_sense<fp32 IQ>")
 }
+
+#define SCN_ROWS_CASE(L, AVG, NAME)                                                                            \
+  case L: {                                                                                                    \
+    out->func = reinterpret_cast<const void*>(&spectrum_sense_kernel<L, SCN_KIND_FLOAT_COMPLEX, false, AVG, true>); \
+    out->threads = Geometry<L>::THREADS;                                                                       \
+    out->smem_bytes = Geometry<L>::kSmemBytes;                                                                 \
+    out->transforms_per_cta = Geometry<L>::F;                                                                  \
+    out->name = NAME "<N2=2^" #L ">";                                                                          \
+    return true;                                                                                               \
+  }
+bool variant_float_rows(int log2n, bool avg, KernelVariant* out) {
+  if (avg) {
+    switch (log2n) {
+      SCN_ROWS_CASE(11, true, "four_step: columns + spectrum_sense_rows<avg> + finalize")
+      SCN_ROWS_CASE(12, true, "four_step: columns + spectrum_sense_rows<avg> + finalize")
+      default: return false;
+    }
+  }
+  switch (log2n) {
+    SCN_ROWS_CASE(11, false, "four_step: columns + spectrum_sense_rows + finalize")
+    SCN_ROWS_CASE(12, false, "four_step: columns + spectrum_sense_rows + finalize")
+    default: return false;
+  }
+}
 }  // namespace scn

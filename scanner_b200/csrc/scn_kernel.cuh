@@ -277,7 +277,9 @@ constexpr int min_ctas() {
 #endif
 }
 
-template <int LOG2N, int KIND, bool DC, bool AVG>
+// ROWS: row mode of the four-step path (scn_large.cu) -- a separate instantiation so that the
+// addressing and the power-out epilogue cost the ordinary kernels nothing.
+template <int LOG2N, int KIND, bool DC, bool AVG, bool ROWS = false>
 __global__ void __launch_bounds__(Geometry<LOG2N>::THREADS, min_ctas<LOG2N, KIND, AVG>())
 spectrum_sense_kernel(const KernelParams p) {
   using G = Geometry<LOG2N>;
@@ -342,10 +344,14 @@ spectrum_sense_kernel(const KernelParams p) {
     const uint32_t s = gg * F + f;
     live = s < p.n_spectra;
     const uint32_t ss = live ? s : 0;
-    // buffer (ss >> rpb_shift) * K + kk, row (ss & mask) inside it; rpb_shift == 0: buffer ss*K + kk
-    const size_t buffer = size_t(ss >> p.rpb_shift) * K + kk;
-    const size_t row = (buffer << p.rpb_shift) + (ss & ((1u << p.rpb_shift) - 1u));
-    return p.raw + row * kBufBytes;
+    if constexpr (ROWS) {
+      // buffer (ss >> rpb_shift) * K + kk, row (ss & mask) inside it
+      const size_t buffer = size_t(ss >> p.rpb_shift) * K + kk;
+      const size_t row = (buffer << p.rpb_shift) + (ss & ((1u << p.rpb_shift) - 1u));
+      return p.raw + row * kBufBytes;
+    } else {
+      return p.raw + (size_t(ss) * K + kk) * kBufBytes;
+    }
   };
   // DC block reduction, warp part: one (si, sq) slot per warp (T >= 32) or per transform (T < 32)
   auto reduce_dc = [&](int si, int sq, int32_t* red) {
@@ -488,7 +494,7 @@ spectrum_sense_kernel(const KernelParams p) {
       if constexpr (AVG) pw[q] = acc[q] = (cur_k == 0) ? pw[q] : __fadd_rn(acc[q], pw[q]);
     }
 
-    if (epilogue_tile && p.power_out != nullptr) {
+    if (ROWS && epilogue_tile) {
       // ---- row mode: averaged power out, detection happens in the finalize kernel -----------------------
       const uint32_t s = cur_g * F + f;
       if (cur_live) {
@@ -496,7 +502,7 @@ spectrum_sense_kernel(const KernelParams p) {
 #pragma unroll
         for (int q = 0; q < kPts; q++) out[t + q * T] = AVG ? __fmul_rn(pw[q], p.inv_averaging) : pw[q];
       }
-    } else if (epilogue_tile) {
+    } else if (!ROWS && epilogue_tile) {
       // ---- dB + detection for spectrum s ----------------------------------------------------------------
       const uint32_t s = cur_g * F + f;
       uint32_t* sm = smask + spar * (F * G::WORDS);
