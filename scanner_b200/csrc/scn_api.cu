@@ -427,6 +427,14 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     if (e == cudaSuccess) e = cudaMemcpy(c->d_window, w.data(), sizeof(float) * cf.sample_count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(e)));
     std::vector<float2> tw = build_twiddles(c->log2n2);
+    if (c->variant.twiddle_layout == 1) {      // warp-per-transform kernel: exp(-2 pi i lane r / N), r = 1..63
+      tw.assign(63 * 32, make_float2(0.f, 0.f));
+      for (int r = 1; r < 64; r++)
+        for (int lane = 0; lane < 32; lane++) {
+          const double a = -2.0 * kPi * double(lane) * double(r) / double(cf.sample_count);
+          tw[size_t(r - 1) * 32 + lane] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    }
     e = cudaMalloc(&c->d_twiddles, sizeof(float2) * tw.size());
     if (e == cudaSuccess) e = cudaMemcpy(c->d_twiddles, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "twiddle upload failed: %s", cudaGetErrorString(e)));

@@ -14,6 +14,7 @@ struct KernelVariant {
   size_t smem_bytes;
   int transforms_per_cta;
   const char* name;
+  int twiddle_layout;     // 0: pass tables of scn_fft.cuh; 1: warp-per-transform table [63][32] of scn_wpt.cuh
 };
 
 // One translation unit per sample kind (compiled in parallel); each fills its rows.
@@ -42,6 +43,7 @@ inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* 
     out->smem_bytes = Geometry<L>::kSmemBytes;                                                \
     out->transforms_per_cta = Geometry<L>::F;                                                 \
     out->name = NAME "<N=2^" #L ">";                                                          \
+    out->twiddle_layout = 0;                                                                  \
     return true;                                                                              \
   }
 

@@ -1,7 +1,21 @@
 // int8 interleaved IQ (HackRF / RTL style, messageQueue.h:218) instantiations.
 #include "scn_dispatch.h"
+#include "scn_wpt.cuh"
+#ifndef SCN_WPT
+#define SCN_WPT 1      // warp-per-transform kernel for N = 2048, K = 1 (the headline workload)
+#endif
 namespace scn {
 bool variant_byte_complex(int log2n, bool dc, bool avg, KernelVariant* out) {
+  if (SCN_WPT && log2n == 11 && !avg) {
+    out->func = dc ? reinterpret_cast<const void*>(&spectrum_sense_wpt_kernel<true>)
+                   : reinterpret_cast<const void*>(&spectrum_sense_wpt_kernel<false>);
+    out->threads = 32 * kWptWarpsPerCta;
+    out->smem_bytes = kWptSmemBytes;
+    out->transforms_per_cta = kWptWarpsPerCta;
+    out->name = dc ? "spectrum_sense_wpt<int8 IQ, dc><N=2^11>" : "spectrum_sense_wpt<int8 IQ><N=2^11>";
+    out->twiddle_layout = 1;
+    return true;
+  }
   if (dc && avg) { SCN_VARIANT_TABLE(SCN_KIND_BYTE_COMPLEX, true, true, "spectrum_sense<int8 IQ, dc, avg>") }
   if (dc) { SCN_VARIANT_TABLE(SCN_KIND_BYTE_COMPLEX, true, false, "spectrum_sense<int8 IQ, dc>") }
   if (avg) { SCN_VARIANT_TABLE(SCN_KIND_BYTE_COMPLEX, false, true, "spectrum_sense<int8 IQ, avg>") }

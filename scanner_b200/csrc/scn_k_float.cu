@@ -13,6 +13,7 @@ bool variant_float_complex(int log2n, bool /*dc*/, bool avg, KernelVariant* out)
     out->smem_bytes = Geometry<L>::kSmemBytes;                                                                 \
     out->transforms_per_cta = Geometry<L>::F;                                                                  \
     out->name = NAME "<N2=2^" #L ">";                                                                          \
+    out->twiddle_layout = 0;                                                                                   \
     return true;                                                                                               \
   }
 bool variant_float_rows(int log2n, bool avg, KernelVariant* out) {
