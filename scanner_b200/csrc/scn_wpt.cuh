@@ -20,7 +20,39 @@ constexpr int kWptN = 2048;
 constexpr int kWptWarpsPerCta = 2;
 // tile padding: 1 float2 per 64 -> lane stride 65 elements: conflict-free 64-bit scatter, unit-stride gather
 __host__ __device__ constexpr int wpt_tile_elems() { return kWptN + (kWptN / 64); }
-constexpr size_t kWptSmemBytes = sizeof(float2) * size_t(wpt_tile_elems()) * kWptWarpsPerCta;
+// Raw staging: the next transform's 4 KB of int8 IQ is fetched by ONE bulk async copy (TMA,
+// cp.async.bulk + mbarrier complete_tx) into a warp-private shared-memory buffer while the current
+// transform is in the FFT; no registers are tied up by the prefetch.
+// Measured on B200 (profiles/README.md): staging costs 32 extra LDS per lane per transform and the
+// tighter register allocation schedules worse -- 405 vs 450 Gsamples/s -- so the default prefetches
+// into 32 registers right after the conversion (issuing them later, after the pass-0 scatter when the
+// register file is nearly empty, measured 423); the TMA path stays as a build option.
+#ifndef SCN_WPT_TMA
+#define SCN_WPT_TMA 0
+#endif
+constexpr size_t kWptRawBytes = size_t(kWptN) * 2;
+constexpr size_t kWptWarpBytes = sizeof(float2) * size_t(wpt_tile_elems()) + (SCN_WPT_TMA ? kWptRawBytes + 16 : 0);
+static_assert(kWptWarpBytes % 16 == 0, "warp region must keep 16-byte alignment");
+constexpr size_t kWptSmemBytes = kWptWarpBytes * kWptWarpsPerCta;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 template <int K>
 __device__ __forceinline__ float2 mul_w64(float2 a) {     // a * W64^K with the trivial cases folded
@@ -103,13 +135,24 @@ __host__ __device__ constexpr int dft64_out_index(int slot) { return (slot >> 3)
 
 // Twiddle table for this variant: tww[(r-1) * 32 + lane] = exp(-2 pi i lane r / 2048), r = 1..63 (host: scn_api.cu).
 template <bool DC>
-__global__ void __launch_bounds__(32 * kWptWarpsPerCta, 4)
+#ifndef SCN_WPT_MINCTAS
+#define SCN_WPT_MINCTAS 4
+#endif
+__global__ void __launch_bounds__(32 * kWptWarpsPerCta, SCN_WPT_MINCTAS)
 spectrum_sense_wpt_kernel(const KernelParams p) {
   constexpr int N = kWptN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+#if !SCN_WPT_TMA
   float2* tile = reinterpret_cast<float2*>(smem_raw) + size_t(warp) * wpt_tile_elems();
+#else
+  unsigned char* wbase = smem_raw + size_t(warp) * kWptWarpBytes;
+  float2* tile = reinterpret_cast<float2*>(wbase);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(wbase + sizeof(float2) * size_t(wpt_tile_elems()));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + sizeof(float2) * size_t(wpt_tile_elems()) + kWptRawBytes);
+  uint32_t phase = 0;
+#endif
   const uint32_t half = N / 2;
   const uint32_t gw = blockIdx.x * kWptWarpsPerCta + warp;          // global warp id
   const uint32_t nw = gridDim.x * kWptWarpsPerCta;
@@ -128,13 +171,28 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
   uint32_t raw[32];                                                  // row r: samples 2*lane, 2*lane+1 (+ 64 r)
   uint32_t s_cur = gw;
   if (s_cur >= p.n_spectra) return;
+#if SCN_WPT_TMA
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, uint32_t(kWptRawBytes));
+    bulk_g2s(stage, p.raw + size_t(s_cur) * kWptRawBytes, uint32_t(kWptRawBytes), bar);
+  }
+  __syncwarp();
+#else
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_cur) * N * 2) + lane;
 #pragma unroll
     for (int r = 0; r < 32; r++) raw[r] = __ldg(src + 32 * r);
   }
+#endif
 
   while (true) {
+#if SCN_WPT_TMA
+    mbar_wait(bar, phase);                        // this transform's bytes have landed
+    phase ^= 1u;
+#pragma unroll
+    for (int r = 0; r < 32; r++) raw[r] = stage[lane + 32 * r];
+#endif
     // ---- DC (warp-local), convert + window ---------------------------------------------------------------
     float2 negc = make_float2(-(kMagic + 128.0f), -(kMagic + 128.0f));
     if constexpr (DC) {
@@ -163,11 +221,20 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     // ---- next transform's loads go in flight now -------------------------------------------------------------
     const uint32_t s_next = s_cur + nw;
     const bool has_next = s_next < p.n_spectra;
+#if SCN_WPT_TMA
+    __syncwarp();                                  // every lane has consumed the staged words
+    if (has_next && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, uint32_t(kWptRawBytes));
+      bulk_g2s(stage, p.raw + size_t(s_next) * kWptRawBytes, uint32_t(kWptRawBytes), bar);
+    }
+#else
     if (has_next) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_next) * N * 2) + lane;
 #pragma unroll
       for (int r = 0; r < 32; r++) raw[r] = __ldg(src + 32 * r);
     }
+#endif
 
     // ---- pass 0: radix-32 on both columns; scatter (Stockham: butterfly j = 2 lane + c -> 32 j + q) ------------
     dft32_inplace<0>(v);
