@@ -157,17 +157,11 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
   const uint32_t gw = blockIdx.x * kWptWarpsPerCta + warp;          // global warp id
   const uint32_t nw = gridDim.x * kWptWarpsPerCta;
 
-  // candidate bins of this lane (process.cpp:46-53): slot s <-> FFT bin j = lane + 32 q(s)
-  uint64_t candbits = 0;
-#pragma unroll
-  for (int s = 0; s < 64; s++) {
-    const uint32_t j = lane + 32 * dft64_out_index(s);
+  // candidate test of process.cpp:46-53 for FFT bin j (evaluated lazily: only slots with a raw hit)
+  auto is_candidate = [&](uint32_t j) -> bool {
     const uint32_t i = j ^ half;
-    bool cand = !(j < p.dc_ignore || (N - j) < p.dc_ignore);
-    cand = cand && !(i < (half - p.use_window) || i > (half + p.use_window));
-    candbits |= uint64_t(cand ? 1u : 0u) << s;
-  }
-
+    return !(j < p.dc_ignore || (N - j) < p.dc_ignore) && !(i < (half - p.use_window) || i > (half + p.use_window));
+  };
   uint32_t raw[32];                                                  // row r: samples 2*lane, 2*lane+1 (+ 64 r)
   uint32_t s_cur = gw;
   if (s_cur >= p.n_spectra) return;
@@ -281,8 +275,6 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
         if (s < 32) hb_lo |= 1u << s; else hb_hi |= 1u << (s - 32);
       }
     }
-    hb_lo &= uint32_t(candbits);
-    hb_hi &= uint32_t(candbits >> 32);
     uint32_t w_lo = 0, w_hi = 0;                   // mask words `lane` and `lane + 32` of this spectrum
     uint32_t total = 0;
     uint32_t any_lo = __reduce_or_sync(0xffffffffu, hb_lo), any_hi = __reduce_or_sync(0xffffffffu, hb_hi);
@@ -292,9 +284,14 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
       while ((rem_lo | rem_hi) != 0u) {            // warp-uniform loop over the slots that have a hit
         int s;
         if (rem_lo) { s = __ffs(rem_lo) - 1; rem_lo &= rem_lo - 1; } else { s = 32 + __ffs(rem_hi) - 1; rem_hi &= rem_hi - 1; }
-        const uint32_t mine = (s < 32) ? (hb_lo >> s) & 1u : (hb_hi >> (s - 32)) & 1u;
+        const int qq = (s >> 3) + 8 * (s & 7);
+        uint32_t mine = (s < 32) ? (hb_lo >> s) & 1u : (hb_hi >> (s - 32)) & 1u;
+        if (mine && !is_candidate(uint32_t(lane) + 32u * qq)) {        // out of band / DC hole: not a hit
+          mine = 0u;
+          if (s < 32) hb_lo &= ~(1u << s); else hb_hi &= ~(1u << (s - 32));
+        }
         const uint32_t b = __ballot_sync(0xffffffffu, mine);
-        const int word = ((s >> 3) + 8 * (s & 7)) ^ 32;
+        const int word = qq ^ 32;
         if (lane == (word & 31)) { if (word < 32) w_lo = b; else w_hi = b; }
       }
       total = __reduce_add_sync(0xffffffffu, __popc(w_lo) + __popc(w_hi));
