@@ -427,6 +427,19 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     if (e == cudaSuccess) e = cudaMemcpy(c->d_window, w.data(), sizeof(float) * cf.sample_count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(e)));
     std::vector<float2> tw = build_twiddles(c->log2n2);
+    if (c->variant.twiddle_layout == 2) {      // scn_p64.cuh: twA[(r-1)*64 + k] = W_4096^(k r); twB[c*128 + t] = W_8192^(t + 128 c)
+      tw.assign(63 * 64 + 32 * 128, make_float2(0.f, 0.f));
+      for (int r = 1; r < 64; r++)
+        for (int k = 0; k < 64; k++) {
+          const double a = -2.0 * kPi * double(k) * double(r) / 4096.0;
+          tw[size_t(r - 1) * 64 + k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+      for (int cc = 0; cc < 32; cc++)
+        for (int t = 0; t < 128; t++) {
+          const double a = -2.0 * kPi * double(t + 128 * cc) / 8192.0;
+          tw[size_t(63 * 64) + size_t(cc) * 128 + t] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    }
     if (c->variant.twiddle_layout == 1) {      // warp-per-transform kernel: exp(-2 pi i lane r / N), r = 1..63
       tw.assign(63 * 32, make_float2(0.f, 0.f));
       for (int r = 1; r < 64; r++)

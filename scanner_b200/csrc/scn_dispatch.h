@@ -14,7 +14,7 @@ struct KernelVariant {
   size_t smem_bytes;
   int transforms_per_cta;
   const char* name;
-  int twiddle_layout;     // 0: pass tables of scn_fft.cuh; 1: warp-per-transform table [63][32] of scn_wpt.cuh
+  int twiddle_layout;     // 0: pass tables of scn_fft.cuh; 1: warp-per-transform table [63][32] of scn_wpt.cuh; 2: scn_p64.cuh tables
 };
 
 // One translation unit per sample kind (compiled in parallel); each fills its rows.

@@ -1,7 +1,20 @@
 // fp32 interleaved IQ (B210 / Airspy style, messageQueue.h:231) instantiations.
 #include "scn_dispatch.h"
+#include "scn_p64.cuh"
+#ifndef SCN_P64
+#define SCN_P64 1      // 64-points-per-thread kernel for N = 8192, K = 1 (BASELINE configs[3])
+#endif
 namespace scn {
 bool variant_float_complex(int log2n, bool /*dc*/, bool avg, KernelVariant* out) {
+  if (SCN_P64 && log2n == 13 && !avg) {
+    out->func = reinterpret_cast<const void*>(&spectrum_sense_p64_kernel);
+    out->threads = kP64Threads;
+    out->smem_bytes = kP64SmemBytes;
+    out->transforms_per_cta = 1;
+    out->name = "spectrum_sense_p64<fp32 IQ><N=2^13>";
+    out->twiddle_layout = 2;
+    return true;
+  }
   if (avg) { SCN_VARIANT_TABLE(SCN_KIND_FLOAT_COMPLEX, false, true, "spectrum_sense<fp32 IQ, avg>") }
   SCN_VARIANT_TABLE(SCN_KIND_FLOAT_COMPLEX, false, false, "spectrum_sense<fp32 IQ>")
 }
