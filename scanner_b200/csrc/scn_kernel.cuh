@@ -40,8 +40,11 @@
 #define SCN_XBUFS_MAXLOG2 13   // ping-pong exchange tiles up to this size, single tile (two barriers) above
 #endif
 #ifndef SCN_WINREG_MAXLOG2
-#define SCN_WINREG_MAXLOG2 16  // window taps live in registers up to this size, L1 loads per tile above
+#define SCN_WINREG_MAXLOG2 13  // window taps live in registers up to this size, L1 loads per tile above
 #endif
+#ifndef SCN_TWMODE_BIG
+#define SCN_TWMODE_BIG 3       // N = 2^14 runs 1024-thread CTAs at 64 registers: the power tree's 1 load per pass
+#endif                         // and no window registers spill least (measured +10-13 %, profiles/README.md)
 
 namespace scn {
 
@@ -382,10 +385,11 @@ spectrum_sense_kernel(const KernelParams p) {
     odcq = int(unsigned(sq) >> LOG2N);
   };
 
-  // twiddles kept in registers for the whole launch (SCN_TWMODE 1 / 2)
-  constexpr bool kHoist1 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 2);
-  constexpr bool kHoist2 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 3);
-  constexpr bool kHoist3 = (SCN_TWMODE == 2) || (SCN_TWMODE == 1 && NP == 4);
+  // twiddles kept in registers for the whole launch (mode 1 / 2)
+  constexpr int kTw = (LOG2N >= 14) ? SCN_TWMODE_BIG : SCN_TWMODE;
+  constexpr bool kHoist1 = (kTw == 2) || (kTw == 1 && NP == 2);
+  constexpr bool kHoist2 = (kTw == 2) || (kTw == 1 && NP == 3);
+  constexpr bool kHoist3 = (kTw == 2) || (kTw == 1 && NP == 4);
   float2 twr1[15], twr2[15], twr3[15];
   if constexpr (kHoist1) load_twiddles<LOG2N, 1>(twr1, p.twiddles, t);
   if constexpr (kHoist2 && NP > 2) load_twiddles<LOG2N, 2>(twr2, p.twiddles, t);
@@ -394,9 +398,9 @@ spectrum_sense_kernel(const KernelParams p) {
 // the scatter/barrier (their loads and products overlap the barrier wait) and applied after the gather.
 #define SCN_TWIDDLE_PREP(P, HOISTED, TWL)                                                \
     if constexpr (!(HOISTED)) {                                                          \
-      if constexpr (SCN_TWMODE == 3 || (SCN_TWMODE == 4 && (P) == NP - 1))               \
+      if constexpr (kTw == 3 || (kTw == 4 && (P) == NP - 1))                             \
         power_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                    \
-      else if constexpr (SCN_TWMODE == 5 || (SCN_TWMODE == 6 && (P) > 1))                \
+      else if constexpr (kTw == 5 || (kTw == 6 && (P) > 1))                              \
         product_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
       else load_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
     }
