@@ -125,9 +125,16 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     if (warp_any) {
 #pragma unroll
       for (int q = 0; q < 64; q++) {
-        if (v[q].x > p.threshold && is_candidate(uint32_t(t) + T * q)) {
-          if (q < 32) hb_lo |= 1u << q; else hb_hi |= 1u << (q - 32);
-        }
+        if (v[q].x > p.threshold) { if (q < 32) hb_lo |= 1u << q; else hb_hi |= 1u << (q - 32); }
+      }
+      // candidate test only for the (few) raw hits of this lane
+      for (uint32_t rest = hb_lo; rest; rest &= rest - 1) {
+        const int q = __ffs(rest) - 1;
+        if (!is_candidate(uint32_t(t) + T * q)) hb_lo &= ~(1u << q);
+      }
+      for (uint32_t rest = hb_hi; rest; rest &= rest - 1) {
+        const int q = __ffs(rest) - 1;
+        if (!is_candidate(uint32_t(t) + T * (q + 32))) hb_hi &= ~(1u << q);
       }
       __syncwarp();
       uint32_t rem_lo = __reduce_or_sync(0xffffffffu, hb_lo), rem_hi = __reduce_or_sync(0xffffffffu, hb_hi);
