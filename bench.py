@@ -435,10 +435,20 @@ def main() -> None:
             tj = json.load(f).get(args.workload)
         if tj and tj["samples_per_launch"] == samples_per_rank:
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    fp32 = None
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            fj = (json.load(f).get(args.workload) or {}).get("fp32_pipe")
+        if fj and traffic is not None:
+            peak_lane = 148 * 128 * 1.965e9                       # FP32 lanes x SMs x max SM clock
+            ach = samples_per_rank * fj["lane_cycles_per_sample"] / (kern_ms * 1e-3)
+            fp32 = {"lane_cycles_per_sample": fj["lane_cycles_per_sample"], "achieved_lane_ops_per_s": ach,
+                    "peak_lane_ops_per_s": peak_lane, "frac": ach / peak_lane, "source": fj["source"],
+                    "note": "secondary roofline: 1-byte IQ is FP32-pipe bound (SURVEY.md H1); informational"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": samples_per_rank * bps,
-                "kernel": ctx.kernel_name, "kernel_ms": kern_ms,
+                "fp32_pipe": fp32, "kernel": ctx.kernel_name, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_sample": bps, "peak_source": peak_src,
                 "kernel_msamples_per_s": samples_per_rank / (kern_ms * 1e-3) / 1e6, "occupancy": info}
 

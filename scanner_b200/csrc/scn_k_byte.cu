@@ -1,11 +1,25 @@
 // int8 interleaved IQ (HackRF / RTL style, messageQueue.h:218) instantiations.
 #include "scn_dispatch.h"
+#include "scn_p64.cuh"
+#ifndef SCN_P64
+#define SCN_P64 1      // 64-points-per-thread kernel with TMA-staged raw buffers for N = 8192, K = 1
+#endif
 #include "scn_wpt.cuh"
 #ifndef SCN_WPT
 #define SCN_WPT 1      // warp-per-transform kernel for N = 2048, K = 1 (the headline workload)
 #endif
 namespace scn {
 bool variant_byte_complex(int log2n, bool dc, bool avg, KernelVariant* out) {
+  if (SCN_P64 && log2n == 13 && !avg) {
+    out->func = dc ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_BYTE_COMPLEX, true>)
+                   : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_BYTE_COMPLEX, false>);
+    out->threads = kP64Threads;
+    out->smem_bytes = p64_smem_bytes<SCN_KIND_BYTE_COMPLEX>();
+    out->transforms_per_cta = 1;
+    out->name = dc ? "spectrum_sense_p64<int8 IQ, dc, tma-staged><N=2^13>" : "spectrum_sense_p64<int8 IQ, tma-staged><N=2^13>";
+    out->twiddle_layout = 2;
+    return true;
+  }
   if (SCN_WPT && log2n == 11 && !avg) {
     out->func = dc ? reinterpret_cast<const void*>(&spectrum_sense_wpt_kernel<true>)
                    : reinterpret_cast<const void*>(&spectrum_sense_wpt_kernel<false>);

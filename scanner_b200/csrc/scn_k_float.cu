@@ -7,9 +7,9 @@
 namespace scn {
 bool variant_float_complex(int log2n, bool /*dc*/, bool avg, KernelVariant* out) {
   if (SCN_P64 && log2n == 13 && !avg) {
-    out->func = reinterpret_cast<const void*>(&spectrum_sense_p64_kernel);
+    out->func = reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_FLOAT_COMPLEX, false>);
     out->threads = kP64Threads;
-    out->smem_bytes = kP64SmemBytes;
+    out->smem_bytes = p64_smem_bytes<SCN_KIND_FLOAT_COMPLEX>();
     out->transforms_per_cta = 1;
     out->name = "spectrum_sense_p64<fp32 IQ><N=2^13>";
     out->twiddle_layout = 2;
