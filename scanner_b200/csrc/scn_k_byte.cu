@@ -2,7 +2,7 @@
 #include "scn_dispatch.h"
 #include "scn_p64.cuh"
 #ifndef SCN_P64
-#define SCN_P64 1      // 64-points-per-thread kernel with TMA-staged raw buffers for N = 8192, K = 1
+#define SCN_P64 1      // 64-points-per-thread kernels with TMA-staged raw buffers for N = 4096 / 8192
 #endif
 #include "scn_wpt.cuh"
 #ifndef SCN_WPT
@@ -10,13 +10,25 @@
 #endif
 namespace scn {
 bool variant_byte_complex(int log2n, bool dc, bool avg, KernelVariant* out) {
-  if (SCN_P64 && log2n == 13 && !avg) {
-    out->func = dc ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_BYTE_COMPLEX, true>)
-                   : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_BYTE_COMPLEX, false>);
-    out->threads = kP64Threads;
-    out->smem_bytes = p64_smem_bytes<SCN_KIND_BYTE_COMPLEX>();
+  if (SCN_P64 && (log2n == 12 || log2n == 13)) {
+    if (log2n == 12) {
+      out->func = dc ? (avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_BYTE_COMPLEX, true, true>)
+                           : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_BYTE_COMPLEX, true, false>))
+                    : (avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_BYTE_COMPLEX, false, true>)
+                           : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_BYTE_COMPLEX, false, false>));
+      out->threads = P64Geometry<12>::T;
+      out->smem_bytes = p64_smem_bytes<12, SCN_KIND_BYTE_COMPLEX>();
+      out->name = "spectrum_sense_p64<int8 IQ, tma-staged><N=2^12>";
+    } else {
+      out->func = dc ? (avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_BYTE_COMPLEX, true, true>)
+                           : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_BYTE_COMPLEX, true, false>))
+                    : (avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_BYTE_COMPLEX, false, true>)
+                           : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_BYTE_COMPLEX, false, false>));
+      out->threads = P64Geometry<13>::T;
+      out->smem_bytes = p64_smem_bytes<13, SCN_KIND_BYTE_COMPLEX>();
+      out->name = "spectrum_sense_p64<int8 IQ, tma-staged><N=2^13>";
+    }
     out->transforms_per_cta = 1;
-    out->name = dc ? "spectrum_sense_p64<int8 IQ, dc, tma-staged><N=2^13>" : "spectrum_sense_p64<int8 IQ, tma-staged><N=2^13>";
     out->twiddle_layout = 2;
     return true;
   }

@@ -2,16 +2,25 @@
 #include "scn_dispatch.h"
 #include "scn_p64.cuh"
 #ifndef SCN_P64
-#define SCN_P64 1      // 64-points-per-thread kernel for N = 8192, K = 1 (BASELINE configs[3])
+#define SCN_P64 1      // 64-points-per-thread kernels for N = 4096 / 8192 (BASELINE configs[2], configs[3])
 #endif
 namespace scn {
 bool variant_float_complex(int log2n, bool /*dc*/, bool avg, KernelVariant* out) {
-  if (SCN_P64 && log2n == 13 && !avg) {
-    out->func = reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<SCN_KIND_FLOAT_COMPLEX, false>);
-    out->threads = kP64Threads;
-    out->smem_bytes = p64_smem_bytes<SCN_KIND_FLOAT_COMPLEX>();
+  if (SCN_P64 && (log2n == 12 || log2n == 13)) {
+    if (log2n == 12) {
+      out->func = avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_FLOAT_COMPLEX, false, true>)
+                      : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<12, SCN_KIND_FLOAT_COMPLEX, false, false>);
+      out->threads = P64Geometry<12>::T;
+      out->smem_bytes = p64_smem_bytes<12, SCN_KIND_FLOAT_COMPLEX>();
+      out->name = "spectrum_sense_p64<fp32 IQ><N=2^12>";
+    } else {
+      out->func = avg ? reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_FLOAT_COMPLEX, false, true>)
+                      : reinterpret_cast<const void*>(&spectrum_sense_p64_kernel<13, SCN_KIND_FLOAT_COMPLEX, false, false>);
+      out->threads = P64Geometry<13>::T;
+      out->smem_bytes = p64_smem_bytes<13, SCN_KIND_FLOAT_COMPLEX>();
+      out->name = "spectrum_sense_p64<fp32 IQ><N=2^13>";
+    }
     out->transforms_per_cta = 1;
-    out->name = "spectrum_sense_p64<fp32 IQ><N=2^13>";
     out->twiddle_layout = 2;
     return true;
   }
