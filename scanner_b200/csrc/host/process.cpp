@@ -32,8 +32,13 @@ ProcessSamples::ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_
 
 ProcessSamples::~ProcessSamples() {}
 
+// Hit records per spectrum copied back with every batch; a spectrum with more hits than this is re-run
+// alone through a full-capacity context (rare: the reference itself treats > 1047 hits as an event,
+// process.cpp:62), so every hit is still reported, in order.
+static const uint32_t kHitCap = 64;
+
 scn_ctx* ProcessSamples::CreateContext(SampleQueue::SampleKind kind, uint32_t enob, bool correctDC,
-                                       uint32_t maxSpectra) {
+                                       uint32_t maxSpectra, uint32_t hitCap) {
   scn_config cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.device = m_device;
@@ -49,7 +54,7 @@ scn_ctx* ProcessSamples::CreateContext(SampleQueue::SampleKind kind, uint32_t en
   cfg.dc_ignore_window = m_dcIgnoreWindow;
   cfg.window = m_window.data();
   cfg.max_spectra = maxSpectra;
-  cfg.max_hits_per_spectrum = 0;                  // == N: every hit is reported, like the reference
+  cfg.max_hits_per_spectrum = hitCap;             // 0 == N
   cfg.flags = SCN_OUT_HITS;
   cfg.ticket_slots = 2;
   scn_ctx* ctx = nullptr;
@@ -90,7 +95,10 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   SampleQueue* q = m_sampleQueue;
   const uint32_t K = (m_mode == FrequencyDomain) ? m_averaging : 1;
   const uint32_t maxSpectra = (m_maxBatch + K - 1) / K;
-  scn_ctx* ctx = CreateContext(q->m_kind, q->GetEnob(), q->GetCorrectDCOffset(), maxSpectra);
+  const uint32_t cap = (m_mode == FrequencyDomain && kHitCap < m_sampleCount) ? kHitCap : m_sampleCount;
+  scn_ctx* ctx = CreateContext(q->m_kind, q->GetEnob(), q->GetCorrectDCOffset(), maxSpectra, cap);
+  scn_ctx* fullCtx = nullptr;                            // lazily created, one spectrum, cap == N
+  std::vector<scn_hit> fullHits;
   const size_t bufBytes = q->GetBufferBytes();
   const uint32_t N = m_sampleCount;
 
@@ -106,7 +114,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   for (auto& s : slot)
     if (scn_alloc_pinned(bufBytes * size_t(maxSpectra) * K, &s.staging) != SCN_OK) Die("scn_alloc_pinned");
   std::vector<uint32_t> counts(maxSpectra);
-  std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * N : 0);
+  std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * cap : 0);
   std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
 
   auto finish = [&](InFlight& f) {
@@ -138,8 +146,20 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
           }
         } else {
           const uint32_t c = counts[s];
+          const scn_hit* list = &hits[size_t(s) * cap];
+          if (c > cap) {                                  // overflow: this spectrum alone, full capacity
+            if (!fullCtx) {
+              fullCtx = CreateContext(q->m_kind, q->GetEnob(), q->GetCorrectDCOffset(), 1, 0);
+              fullHits.resize(N);
+            }
+            uint32_t c2 = 0;
+            if (scn_process_host(fullCtx, static_cast<char*>(f.staging) + size_t(s) * K * bufBytes, 1, nullptr, nullptr,
+                                 &c2, fullHits.data(), nullptr) != SCN_OK)
+              Die("scn_process_host");
+            list = fullHits.data();
+          }
           for (uint32_t r = 0; r < c && r < N; r++) {
-            const scn_hit& h = hits[size_t(s) * N + r];
+            const scn_hit& h = list[r];
             const uint64_t hz = scn_hit_frequency(header.m_frequency, m_sampleRate, N, h.bin);
             if (m_out) fprintf(m_out, "freq %lu power_db %f\n", (unsigned long)hz, h.power_db);   // process.cpp:57
             if (m_sink) m_sink(Detection{header.m_sequenceId, header.m_frequency, hz, h.power_db, h.bin});
@@ -195,6 +215,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
     }
   }
   for (auto& s : slot) scn_free_pinned(s.staging);
+  if (fullCtx) scn_destroy(fullCtx);
   scn_destroy(ctx);
 }
 
@@ -217,7 +238,7 @@ void ProcessSamples::Run(int16_t sample_buffer[][2], uint32_t centerFrequency) {
   // Synchronous single-buffer path (process.cpp:131-144): convert -> window -> FFT -> detect on raw
   // int16 IQ.  (The reference's version dereferences a null header in process_fft and crashes;
   // here the centre frequency argument is used.)
-  scn_ctx* ctx = CreateContext(SampleQueue::ShortComplex, m_enob, false, 1);
+  scn_ctx* ctx = CreateContext(SampleQueue::ShortComplex, m_enob, false, 1, 0);
   std::vector<uint32_t> count(1);
   std::vector<scn_hit> hits(m_sampleCount);
   if (m_mode == FrequencyDomain) {

@@ -58,7 +58,8 @@ class ProcessSamples {
  private:
   static const uint32_t MAX_THREADS = 8;
   void ThreadWorker(uint32_t threadId);
-  scn_ctx* CreateContext(SampleQueue::SampleKind kind, uint32_t enob, bool correctDC, uint32_t maxSpectra);
+  scn_ctx* CreateContext(SampleQueue::SampleKind kind, uint32_t enob, bool correctDC, uint32_t maxSpectra,
+                         uint32_t hitCap);
   void TimeToString(time_t t, char* buffer, uint32_t length);
   void ProcessWrite(bool doWrite, double centerFrequency, uint64_t sequenceId);
 

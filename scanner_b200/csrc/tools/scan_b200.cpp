@@ -125,6 +125,47 @@ int main(int argc, char** argv) {
             (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount());
     return 0;
   }
+  if (cmd == "bench" && argc >= 8) {
+    // scan_b200 bench <kind> <N> <enob> <dc> <distinct_buffers> <total_buffers> [threads] [max_batch]
+    // Throughput of the plugin surface itself: a ReplaySource cycling over `distinct` synthetic buffers pushes
+    // `total` raw buffers through SampleQueue into GPU ProcessSamples workers (printing off).
+    const int kind = atoi(argv[2]);
+    const uint32_t n = atoi(argv[3]), enob = atoi(argv[4]);
+    const bool dc = atoi(argv[5]) != 0;
+    const size_t distinct = strtoull(argv[6], nullptr, 0), total = strtoull(argv[7], nullptr, 0);
+    const uint32_t threads = argc > 8 ? atoi(argv[8]) : 2;
+    const uint32_t maxBatch = argc > 9 ? atoi(argv[9]) : 4096;
+    const uint32_t fs = 20000000;
+    const size_t bb = SyntheticSource::BufferBytes(SampleQueue::SampleKind(kind), n);
+    std::vector<char> pool(distinct * bb);
+    {
+      SyntheticSource gen(SampleQueue::SampleKind(kind), enob ? enob : 12, 1234, 1, fs, n, 2.4e9, 0.0);
+      for (size_t b = 0; b < distinct; b++) gen.Generate(0, 0, uint32_t(b), pool.data() + b * bb);
+    }
+    std::vector<char> raw(total * bb);
+    std::vector<double> freqs(total);
+    for (size_t b = 0; b < total; b++) {
+      memcpy(raw.data() + b * bb, pool.data() + (b % distinct) * bb, bb);
+      freqs[b] = 2.4075e9 + 15e6 * double(b % 50);
+    }
+    ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs.data(), total, 0, fs, n);
+    ProcessSamples process(n, fs, enob, 25.0f, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
+    process.SetOutput(nullptr);
+    process.SetMaxBatch(maxBatch);
+    SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 4 * maxBatch, dc, false);
+    queue.SetDropFirstSweep(false);
+    const auto t0 = std::chrono::steady_clock::now();
+    source.Start();
+    source.StartStreaming(1, queue);
+    process.StartProcessing(queue);
+    source.Join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("plugin-surface throughput: %.1f Msamples/s (%zu buffers of %u samples, kind %d, %u worker threads, "
+           "batch <= %u, %lu hits, %lu launches, %.3f s)\n",
+           double(total) * n / sec / 1e6, total, n, kind, threads, maxBatch, (unsigned long)process.GetHitCount(),
+           (unsigned long)process.GetLaunchCount(), sec);
+    return 0;
+  }
   fprintf(stderr, "scan_b200: bad arguments\n");
   return 2;
 }
