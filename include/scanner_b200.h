@@ -183,6 +183,20 @@ SCN_API int scn_summarize_steps(scn_ctx* ctx, const uint32_t* d_hit_mask, const 
 SCN_API int scn_merge_step_records(scn_ctx* ctx, const uint32_t* d_parts, uint32_t n_parts,
                                    uint32_t n_steps, uint32_t* d_out, void* stream);
 
+/* ---- HackRF sweep-frame pre-pass (replaces HackRFSource::interpolateSamples, hackRFSource.cpp:186-222) ----
+ * d_transfers: n_transfers sweep-mode transfers of valid_length bytes each, int8 IQ, device
+ * resident, patched IN PLACE exactly as the reference patches them (frame header 0x7F 0x7F + LE64
+ * frequency parsed from the first block; samples 0..4 overwritten with sample 5, including the
+ * reference's later-iteration quirk).  d_frequency_hz[t] = header frequency (0 if no header); the
+ * centre frequency the reference hands the queue is double(frequency + m_scanOffset),
+ * m_scanOffset = uint32(uint32(0.75 * sample_rate) / 2.0) (hackRFSource.cpp:111-112,221).
+ * d_status[t]: bit 0 = header seen, bits 8.. = number of "frequencyHz != thisFrequencyHz" lines
+ * the reference would have printed.  Either output may be NULL.  Afterwards every transfer is
+ * valid_length / (2 * sample_count) consecutive buffers for scn_launch_device. */
+SCN_API int scn_hackrf_prepass_device(scn_ctx* ctx, void* d_transfers, uint32_t n_transfers,
+                                      uint32_t valid_length, uint64_t* d_frequency_hz,
+                                      uint32_t* d_status, void* stream);
+
 /* ---- Host-side helpers that restate reference arithmetic --------------------- */
 /* uint32_t(useBandWidth * N / 2.0), process.cpp:85. */
 SCN_API uint32_t scn_use_window(double use_bandwidth, uint32_t sample_count);

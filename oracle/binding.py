@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
         h.orc_bench.argtypes = [_U32, _U32, _U32, _U32, _U32, _U32, _F, _U32, _U32, _VP, _VP, _U32, _U32,
                                 _U32, _I, _VP]
         h.orc_hardware_threads.restype = _U32
+        h.orc_hackrf_prepass.argtypes = [_VP, _U32, _U32, _VP, _VP]
+        h.orc_hackrf_prepass.restype = None
         h.orc_hardware_threads.argtypes = []
         _lib = h
     return _lib
@@ -180,6 +182,16 @@ def bench(raw: np.ndarray, n: int, sample_rate: int, enob: int, kind: int, corre
                           use_window_bins, dc_ignore_window, _p(window), _p(raw), nb, repeats, threads,
                           1 if faithful else 0, C.byref(hits))
     return float(sec), int(hits.value), threads
+
+
+def hackrf_prepass(transfers: np.ndarray, valid_length: int):
+    """Returns (patched copy, frequency_hz uint64[T], status uint32[T]) -- hackRFSource.cpp:186-222."""
+    buf = np.array(transfers, dtype=np.uint8, copy=True).reshape(-1)
+    nt = buf.size // valid_length
+    freq = np.zeros(nt, np.uint64)
+    status = np.zeros(nt, np.uint32)
+    lib().orc_hackrf_prepass(_p(buf), nt, valid_length, _p(freq), _p(status))
+    return buf.reshape(nt, valid_length), freq, status
 
 
 def hardware_threads() -> int:

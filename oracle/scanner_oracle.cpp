@@ -584,4 +584,39 @@ ORC_API void orc_time_domain(uint32_t n, uint32_t enob, uint32_t kind, uint32_t 
   }
 }
 
+// HackRF sweep-frame pre-pass -- HackRFSource::interpolateSamples, hackRFSource.cpp:186-222, restated
+// with its quirks: the block loop runs valid_length/2/8192 times but always inspects the FIRST block
+// (`ubuf` is never advanced, :192), so iterations after the first only act when the patched bytes
+// themselves read 0x7F 0x7F (sample 5 saturated); the patch value is sample 5, averaged for i > 0 with
+// sample i-1 in int arithmetic (truncating toward zero, :209-210) and narrowed to int8; samples 0..4
+// are overwritten in place (:213-216).  frequency_hz[t] = the last header value (0 if none; the
+// source adds m_scanOffset, :221); status[t] bit 0 = a header was seen, bits 8.. = number of
+// "frequencyHz != thisFrequencyHz" prints (:202-206).
+ORC_API void orc_hackrf_prepass(uint8_t* transfers, uint32_t n_transfers, uint32_t valid_length,
+                                uint64_t* frequency_hz, uint32_t* status) {
+  for (uint32_t t = 0; t < n_transfers; t++) {
+    uint8_t* ubuf = transfers + size_t(t) * valid_length;
+    const uint32_t count = valid_length / 2;
+    uint64_t freq = 0;
+    uint32_t st = 0;
+    for (uint32_t i = 0; i < count; i += 8192) {
+      if (ubuf[0] == 0x7F && ubuf[1] == 0x7F) {
+        uint64_t cur = 0;
+        for (int k = 7; k >= 0; k--) cur = (cur << 8) | ubuf[2 + k];
+        if (freq != 0 && freq != cur) st += 1u << 8;
+        freq = cur;
+        st |= 1u;
+        int8_t post[2] = {int8_t(ubuf[10]), int8_t(ubuf[11])};
+        if (i > 0) {
+          post[0] = int8_t((int(post[0]) + int(int8_t(ubuf[2 * (i - 1)]))) / 2);
+          post[1] = int8_t((int(post[1]) + int(int8_t(ubuf[2 * (i - 1) + 1]))) / 2);
+        }
+        for (uint32_t j = 0; j < 5; j++) { ubuf[2 * j] = uint8_t(post[0]); ubuf[2 * j + 1] = uint8_t(post[1]); }
+      }
+    }
+    if (frequency_hz) frequency_hz[t] = freq;
+    if (status) status[t] = st;
+  }
+}
+
 ORC_API uint32_t orc_hardware_threads() { return std::thread::hardware_concurrency(); }

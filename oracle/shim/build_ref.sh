@@ -20,9 +20,17 @@ done
 $CXX $FLAGS -c "$REF/fft.cpp" -o "$OUT/fft.o"
 $CXX $FLAGS -c "$REF/process.cpp" -o "$OUT/process.o"
 $CXX $FLAGS -c "$REF/frequencyTable.cpp" -o "$OUT/frequencyTable.o"
+# signalSource.cpp:36-38 (Start/Stop) and hackRFSource.cpp:150-178 (set_sample_rate) are non-void functions
+# without a return statement: at -O2 gcc drops the epilogue and control runs on into the next function
+# (observed: the constructor never returns), and gcc 13's -O0 default plants a trap there instead.
+# -O0 -fno-unreachable-traps keeps the plain epilogue; the only arithmetic in these two files is the integer
+# header parse / sample patch of hackRFSource.cpp:186-222, which -O0 does not change.
+$CXX $FLAGS -O0 -fno-unreachable-traps -c "$REF/signalSource.cpp" -o "$OUT/signalSource.o"
+$CXX $FLAGS -O0 -fno-unreachable-traps -c "$REF/hackRFSource.cpp" -o "$OUT/hackRFSource.o"
 $CXX $FLAGS -c "$HERE/shim_impl.cpp" -o "$OUT/shim_impl.o"
+$CXX $FLAGS -c "$HERE/shim_hackrf.cpp" -o "$OUT/shim_hackrf.o"
 $CXX $FLAGS -c "$HERE/ref_tool.cpp" -o "$OUT/ref_tool.o"
-$CXX -pthread -o "$OUT/ref_tool" "$OUT/ref_tool.o" "$OUT/utility.o" "$OUT/fft.o" "$OUT/process.o" "$OUT/frequencyTable.o" "$OUT/shim_impl.o"
-$CXX -pthread -o "$OUT/ref_tool_cmath" "$OUT/ref_tool.o" "$OUT/utility_cmath.o" "$OUT/fft.o" "$OUT/process.o" "$OUT/frequencyTable.o" "$OUT/shim_impl.o"
+$CXX -pthread -o "$OUT/ref_tool" "$OUT/ref_tool.o" "$OUT/utility.o" "$OUT/fft.o" "$OUT/process.o" "$OUT/frequencyTable.o" "$OUT/signalSource.o" "$OUT/hackRFSource.o" "$OUT/shim_impl.o" "$OUT/shim_hackrf.o"
+$CXX -pthread -o "$OUT/ref_tool_cmath" "$OUT/ref_tool.o" "$OUT/utility_cmath.o" "$OUT/fft.o" "$OUT/process.o" "$OUT/frequencyTable.o" "$OUT/signalSource.o" "$OUT/hackRFSource.o" "$OUT/shim_impl.o" "$OUT/shim_hackrf.o"
 rm -f "$OUT"/*.o
 echo "oracle/_ref: built ref_tool, ref_tool_cmath from $REF"

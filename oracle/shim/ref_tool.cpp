@@ -11,7 +11,16 @@
 //        producer thread and runs ProcessSamples::StartProcessing (process.cpp:316) with ONE worker
 //        (the reference's two workers race on the shared FFT object, fft.cpp:20-25);
 //        stdout is the reference's own output ("Start scan at ...", "freq %lu power_db %f", ...).
+//   ref_tool hackrf_prepass <N> <fs> <start> <stop> <valid_length> <in_file> <out_file>
+//        runs HackRFSource::interpolateSamples (hackRFSource.cpp:186-222) on every transfer of
+//        <in_file>; <out_file> = per transfer { double returned centre frequency, patched bytes };
+//        stdout carries the function's own mismatch prints.
+//   ref_tool hackrf_scan <N> <fs> <start> <stop> <threshold> <iterations> <valid_length> <stream_file>
+//        the whole HackRF flow with the settings of scan.cpp:177-188,211-223: transfers are delivered
+//        to the rx callback the source registers (hackRFSource.cpp:180-264) -> SampleQueue ->
+//        ProcessSamples (one worker); stdout is the reference's own output.
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 #include <stdio.h>
 #include <math.h>
@@ -30,6 +39,9 @@
 #include "messageQueue.h"
 #include "signalSource.h"
 #include "process.h"
+#define class struct   // interpolateSamples is a private member of `class HackRFSource` (access only; the source is unmodified)
+#include "hackRFSource.h"
+#undef class
 
 static std::vector<char> read_all(FILE* f) {
   std::vector<char> data;
@@ -127,6 +139,50 @@ int main(int argc, char** argv) {
     producer.join();
     fflush(stdout);
     return 0;
+  }
+  if (cmd == "hackrf_prepass" && argc == 9) {
+    uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));
+    double start = atof(argv[4]), stop = atof(argv[5]);
+    size_t valid = strtoul(argv[6], nullptr, 0);
+    std::vector<char> stream = read_file(argv[7]);
+    FILE* out = fopen(argv[8], "wb");
+    if (!out) { fprintf(stderr, "ref_tool: cannot write %s\n", argv[8]); return 2; }
+    HackRFSource source("hackrf", fs, n, start, stop);
+    for (size_t off = 0; off + valid <= stream.size(); off += valid) {
+      hackrf_transfer t;
+      memset(&t, 0, sizeof(t));
+      t.buffer = reinterpret_cast<uint8_t*>(stream.data() + off);
+      t.buffer_length = t.valid_length = int(valid);
+      double f = source.interpolateSamples(&t);
+      fwrite(&f, sizeof(f), 1, out);
+      fwrite(t.buffer, 1, valid, out);
+    }
+    fclose(out);
+    fflush(stdout);
+    _exit(0);   // ~HackRFSource prints through a bad format; nothing left to flush
+  }
+  if (cmd == "hackrf_scan" && argc == 10) {
+    uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));
+    double start = atof(argv[4]), stop = atof(argv[5]);
+    float threshold = float(atof(argv[6]));
+    uint32_t iterations = atoi(argv[7]);
+    size_t valid = strtoul(argv[8], nullptr, 0);
+    std::vector<char> stream = read_file(argv[9]);
+    HackRFSource* source = new HackRFSource("hackrf", fs, n, start, stop);
+    // scan.cpp:182-188: enob 8, DC correction on, ByteComplex, dcIgnoreWidth forced to 0
+    ProcessSamples process(n, fs, 8, threshold, gr::fft::window::WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, 1);
+    SampleQueue queue(SampleQueue::ByteComplex, 8, n, 1024, true, false);
+    source->StartStreaming(iterations, queue);
+    std::thread feeder([&]() {
+      for (size_t off = 0; off + valid <= stream.size() && !shim_hackrf_rx_stopped(); off += valid)
+        shim_hackrf_deliver(reinterpret_cast<uint8_t*>(stream.data() + off), int(valid));
+      for (int spin = 0; spin < 2000 && !shim_hackrf_rx_stopped(); spin++) usleep(1000);
+      if (!shim_hackrf_rx_stopped()) { fprintf(stderr, "ref_tool: stream ended before the source finished\n"); _exit(3); }
+    });
+    process.StartProcessing(queue);
+    feeder.join();
+    fflush(stdout);
+    _exit(0);
   }
   fprintf(stderr, "ref_tool: bad arguments\n");
   return 2;

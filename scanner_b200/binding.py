@@ -72,6 +72,7 @@ SYMBOLS = [
     ("scn_record_words", _U32, [_VP]),
     ("scn_summarize_steps", _I, [_VP, _VP, _VP, _U32, _U64, _U32, _U32, _VP, _VP]),
     ("scn_merge_step_records", _I, [_VP, _VP, _U32, _U32, _VP, _VP]),
+    ("scn_hackrf_prepass_device", _I, [_VP, _VP, _U32, _U32, _VP, _VP, _VP]),
     ("scn_use_window", _U32, [_D, _U32]),
     ("scn_hit_frequency", _U64, [_D, _U32, _U32, _U32]),
     ("scn_frequency_table", _U32, [_U32, _D, _D, _D, _D, C.POINTER(_D), _U32]),
@@ -273,6 +274,13 @@ class SpectrumSense:
     def merge_step_records(self, d_parts: int, n_parts: int, n_steps: int, d_out: int, stream: int = 0) -> None:
         _check(self._lib.scn_merge_step_records(self._ctx, _VP(d_parts), n_parts, n_steps, _VP(d_out),
                                                 _VP(stream or None)))
+
+    def hackrf_prepass_device(self, d_transfers: int, n_transfers: int, valid_length: int,
+                              d_frequency_hz: int = 0, d_status: int = 0, stream: int = 0) -> None:
+        """In-place HackRF sweep-frame pre-pass over device-resident transfers (hackRFSource.cpp:186-222)."""
+        _check(self._lib.scn_hackrf_prepass_device(self._ctx, _VP(d_transfers or None), n_transfers, valid_length,
+                                                   _VP(d_frequency_hz or None), _VP(d_status or None),
+                                                   _VP(stream or None)))
 
     @property
     def record_words(self) -> int:

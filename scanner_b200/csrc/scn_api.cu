@@ -20,6 +20,8 @@ namespace scn {
 cudaError_t launch_summarize(const uint32_t* masks, const uint32_t* counts, uint32_t n_spectra,
                              uint64_t first_unit, uint32_t units_per_step, uint32_t n_steps, uint32_t words,
                              uint32_t* records, int num_sms, cudaStream_t stream);
+cudaError_t launch_hackrf_prepass(void* transfers, uint32_t n_transfers, uint32_t valid_length,
+                                  uint64_t* frequency_hz, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_merge(const uint32_t* parts, uint32_t n_parts, uint32_t n_steps, uint32_t rec_words,
                          uint32_t* out, cudaStream_t stream);
 // scn_large.cu: four-step path for N = 2^15, 2^16
@@ -674,6 +676,20 @@ SCN_API int scn_merge_step_records(scn_ctx* c, const uint32_t* d_parts, uint32_t
   SCN_CUDA(cudaSetDevice(c->cfg.device));
   SCN_CUDA(scn::launch_merge(d_parts, n_parts, n_steps, c->words + 2, d_out, static_cast<cudaStream_t>(stream)));
   c->launches++;
+  return SCN_OK;
+}
+
+SCN_API int scn_hackrf_prepass_device(scn_ctx* c, void* d_transfers, uint32_t n_transfers, uint32_t valid_length,
+                                      uint64_t* d_frequency_hz, uint32_t* d_status, void* stream) {
+  if (!c || (n_transfers && !d_transfers)) return fail(SCN_ERR_INVALID, "hackrf_prepass: bad arguments");
+  if (c->cfg.sample_kind != SCN_KIND_BYTE_COMPLEX)
+    return fail(SCN_ERR_INVALID, "hackrf_prepass: HackRF transfers are int8 IQ (SCN_KIND_BYTE_COMPLEX)");
+  if (valid_length < 12 || valid_length % (2 * c->cfg.sample_count) != 0)
+    return fail(SCN_ERR_INVALID, "hackrf_prepass: valid_length must be a whole number of sample_count buffers");
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  SCN_CUDA(scn::launch_hackrf_prepass(d_transfers, n_transfers, valid_length, d_frequency_hz, d_status,
+                                      static_cast<cudaStream_t>(stream)));
+  if (n_transfers) c->launches++;
   return SCN_OK;
 }
 

@@ -6,11 +6,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "buffer.h"
 #include "frequencyTable.h"
+#include "hackrfSweepSource.h"
 #include "sampleBuffer.h"
 #include "sampleQueue.h"
 #include "syntheticSource.h"
@@ -25,7 +27,73 @@ struct CountingVisitor : ProcessInterface<uint8_t> {
   void End() override { ends++; CHECK(seen == total); }
 };
 
-int main() {
+static std::vector<char> ReadAll(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
+  std::vector<char> data;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  return data;
+}
+
+// host_selftest hackrf_prepass <N> <fs> <start> <stop> <valid_length> <in_file> <out_file>
+//   HackRFSweepSource::InterpolateSamples on every transfer; output format of `ref_tool hackrf_prepass`.
+// host_selftest hackrf_queue <N> <fs> <start> <stop> <iterations> <valid_length> <stream_file> <out_file>
+//   replays the capture through RxCallback into a SampleQueue (no GPU) and dumps, per accepted message,
+//   { double frequency, int64 time, uint64 sequenceId, raw bytes }.
+static int HackrfModes(int argc, char** argv) {
+  const std::string cmd = argv[1];
+  const uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));
+  const double start = atof(argv[4]), stop = atof(argv[5]);
+  if (cmd == "hackrf_prepass" && argc == 9) {
+    const uint32_t valid = uint32_t(strtoul(argv[6], nullptr, 0));
+    std::vector<char> stream = ReadAll(argv[7]);
+    FILE* out = fopen(argv[8], "wb");
+    CHECK(out != nullptr);
+    HackRFSweepSource source("hackrf", fs, n, start, stop);
+    for (size_t off = 0; off + valid <= stream.size(); off += valid) {
+      uint8_t* p = reinterpret_cast<uint8_t*>(stream.data() + off);
+      const double f = source.InterpolateSamples(p, valid);
+      fwrite(&f, sizeof(f), 1, out);
+      fwrite(p, 1, valid, out);
+    }
+    fclose(out);
+    return 0;
+  }
+  if (cmd == "hackrf_queue" && argc == 10) {
+    const uint32_t iterations = atoi(argv[6]);
+    const uint32_t valid = uint32_t(strtoul(argv[7], nullptr, 0));
+    std::vector<char> stream = ReadAll(argv[8]);
+    FILE* out = fopen(argv[9], "wb");
+    CHECK(out != nullptr);
+    HackRFSweepSource source("hackrf", fs, n, start, stop);
+    source.SetCapture(reinterpret_cast<uint8_t*>(stream.data()), stream.size(), valid);
+    source.SetReplayClock(1500000000, 1000);
+    SampleQueue queue(SampleQueue::ByteComplex, 8, n, uint32_t(stream.size() / (2 * n)) + 8, true, false);
+    source.StartStreaming(iterations, queue);
+    source.Join();
+    CHECK(source.GetStreamDone());
+    while (SampleQueue::MessageType* m = queue.GetNextSamples()) {
+      const double f = m->GetHeader().m_frequency;
+      const int64_t t = int64_t(m->GetHeader().m_time);
+      const uint64_t seq = m->GetHeader().m_sequenceId;
+      fwrite(&f, sizeof(f), 1, out);
+      fwrite(&t, sizeof(t), 1, out);
+      fwrite(&seq, sizeof(seq), 1, out);
+      fwrite(m->GetData(), 1, m->GetDataBytes(), out);
+      queue.MessageProcessed(m);
+    }
+    fclose(out);
+    return 0;
+  }
+  fprintf(stderr, "host_selftest: bad arguments\n");
+  return 2;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1) return HackrfModes(argc, argv);
   // ---- FrequencyTable (frequencyTable.cpp:9-47)
   FrequencyTable ft(20000000, 2.4e9, 3.15e9, 0.75, 0.0, false);
   CHECK(ft.GetFrequencyCount() == 50);

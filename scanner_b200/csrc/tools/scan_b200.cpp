@@ -8,6 +8,9 @@
 //   scan_b200 synth <kind> <N> <fs> <enob> <dc> <threshold> <start> <stop> <buffers_per_step>
 //                   <iterations> <seed> [threads] [averaging]
 //       seeded SyntheticSource sweep (first sweep dropped like the reference: needs iterations >= 2).
+//   scan_b200 hackrf <N> <fs> <start> <stop> <threshold> <iterations> <valid_length> <stream_file> [threads]
+//       same arguments and capture file as oracle/_ref/ref_tool hackrf_scan: HackRFSweepSource replays the
+//       sweep-mode transfers with scan.cpp:177-188's settings (enob 8, DC correction on, ByteComplex).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +19,7 @@
 #include <vector>
 
 #include "buffer.h"
+#include "hackrfSweepSource.h"
 #include "process.h"
 #include "sampleBuffer.h"
 #include "sampleQueue.h"
@@ -95,6 +99,25 @@ int main(int argc, char** argv) {
     SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
     source.Start();
     source.StartStreaming(1, queue);
+    process.StartProcessing(queue);
+    source.Join();
+    fflush(stdout);
+    return 0;
+  }
+  if (cmd == "hackrf" && argc >= 10) {
+    const uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));
+    const double start = atof(argv[4]), stop = atof(argv[5]);
+    const float thr = float(atof(argv[6]));
+    const uint32_t iterations = atoi(argv[7]);
+    const uint32_t valid = uint32_t(strtoul(argv[8], nullptr, 0));
+    std::vector<char> stream = ReadFile(argv[9]);
+    const uint32_t threads = argc > 10 ? atoi(argv[10]) : 1;
+    HackRFSweepSource source("hackrf", fs, n, start, stop);
+    source.SetCapture(reinterpret_cast<uint8_t*>(stream.data()), stream.size(), valid);
+    source.SetReplayClock(1500000000, 1000);
+    ProcessSamples process(n, fs, 8, thr, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
+    SampleQueue queue(SampleQueue::ByteComplex, 8, n, 1024, true, false);
+    source.StartStreaming(iterations, queue);
     process.StartProcessing(queue);
     source.Join();
     fflush(stdout);
