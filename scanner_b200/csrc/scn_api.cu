@@ -101,6 +101,7 @@ struct scn_ctx {
   uint32_t hit_cap = 0;
   float onebymax = 1.0f;
   float* d_window = nullptr;
+  bool win_mirror = false;       // window[n] == window[N-1-n] bitwise
   float* d_ones = nullptr;       // unit window for the row transforms of the four-step path
   float2* d_twiddles = nullptr;
   scn::KernelVariant variant{};
@@ -214,6 +215,7 @@ int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d
   p.threshold = c->cfg.threshold;
   p.use_window = c->cfg.use_window;
   p.dc_ignore = c->cfg.dc_ignore_window;
+  p.win_mirror = c->win_mirror ? 1u : 0u;
   const uint32_t F = uint32_t(c->variant.transforms_per_cta);
   const uint32_t n_groups = (n_spectra + F - 1) / F;
   uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
@@ -425,6 +427,9 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     std::vector<float> w(cf.sample_count);
     const float s = (cf.sample_kind == SCN_KIND_FLOAT_COMPLEX) ? 1.0f : c->onebymax;
     for (uint32_t i = 0; i < cf.sample_count; i++) w[i] = cf.window[i] * s;
+    c->win_mirror = true;
+    for (uint32_t i = 0; i < cf.sample_count / 2 && c->win_mirror; i++)
+      c->win_mirror = memcmp(&w[i], &w[cf.sample_count - 1 - i], sizeof(float)) == 0;
     e = cudaMalloc(&c->d_window, sizeof(float) * cf.sample_count);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_window, w.data(), sizeof(float) * cf.sample_count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(e)));

@@ -25,6 +25,61 @@
 
 namespace scn {
 
+// Raw IQ is read exactly once.  SCN_STREAM_LOADS=1 loads it through the read-only path WITHOUT allocating in L1
+// (ld.global.nc.L1::no_allocate), meant to keep the streaming data from evicting the window / twiddle tables.
+// Measured on B200 (tools/kbench.py A/B): no gain for the 1- and 2-byte kinds and 3 % SLOWER for fp32 IQ at
+// N = 4096 / 8192, so the default stays the plain __ldg path; what fixed the table misses at N = 8192 was
+// halving the table footprint (scn_p64.cuh).
+#ifndef SCN_STREAM_LOADS
+#define SCN_STREAM_LOADS 0
+#endif
+__device__ __forceinline__ unsigned short ldg_stream(const unsigned short* p) {
+#if SCN_STREAM_LOADS
+  unsigned short v;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ unsigned int ldg_stream(const unsigned int* p) {
+#if SCN_STREAM_LOADS
+  unsigned int v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
+#if SCN_STREAM_LOADS
+  uint2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+#if SCN_STREAM_LOADS
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+#if SCN_STREAM_LOADS
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 constexpr int kPts = 16;   // complex points per thread
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }

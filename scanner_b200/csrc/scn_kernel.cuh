@@ -68,6 +68,9 @@ struct KernelParams {
   // writing fp32 power [row][N] to power_out.  rpb_shift == 0 and power_out == nullptr otherwise.
   uint32_t rpb_shift;
   float* __restrict__ power_out;
+  // 1 when window[n] == window[N-1-n] bit for bit (every gr-fft window is): kernels whose tables overflow L1
+  // (scn_p64.cuh at N = 8192) then read taps n >= N/2 from the mirrored address, halving the table footprint.
+  uint32_t win_mirror;
 };
 
 // dB = 10*log2(sqrt(p))/log2(10) = (5/log2(10)) * log2(p)
@@ -125,16 +128,16 @@ struct RawTile {
   template <int NB>
   static __device__ __forceinline__ void load_run(const uint8_t* __restrict__ p, uint32_t* dst) {
     if constexpr (NB == 2) {
-      dst[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
+      dst[0] = ldg_stream(reinterpret_cast<const unsigned short*>(p));
     } else if constexpr (NB == 4) {
-      dst[0] = __ldg(reinterpret_cast<const unsigned int*>(p));
+      dst[0] = ldg_stream(reinterpret_cast<const unsigned int*>(p));
     } else if constexpr (NB == 8) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+      const uint2 v = ldg_stream(reinterpret_cast<const uint2*>(p));
       dst[0] = v.x; dst[1] = v.y;
     } else {
 #pragma unroll
       for (int i = 0; i < NB / 16; i++) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(p) + i);
         dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
       }
     }

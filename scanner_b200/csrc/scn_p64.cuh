@@ -45,6 +45,9 @@ constexpr size_t p64_smem_bytes() {
 }
 // twiddle tables (host: scn_api.cu, layout 2): twA[(r-1)*64 + k] = exp(-2 pi i k r / 4096), r = 1..63, k < 64;
 //                                             twB[c*128 + t]    = exp(-2 pi i (t + 128 c) / 8192), c < 32, t < 128
+// (the kernel reads rows c < 16 only: row c + 16 is row c times -i, applied for free in the butterfly -- with the
+//  mirrored window taps this brings the per-CTA table working set from 78 KB to 39 KB, inside the 64 KB of L1
+//  that two 66 KB CTAs leave; ncu had the tables hitting L1 only 34 % of the time)
 constexpr int kP64TwAElems = 63 * 64;
 constexpr int kP64TwBElems = 32 * 128;
 
@@ -78,6 +81,17 @@ spectrum_sense_p64_kernel(const KernelParams p) {
   const uint32_t K = AVG ? p.averaging : 1u;
   uint32_t spar = 0, phase = 0, tpar = 0;
   int dci = 0, dcq = 0;
+
+  // window tap of sample t + T r.  N = 8192 only (its tables overflow L1, N = 4096's do not and its K > 1 variant
+  // has no register to spare): taps of the upper half come from the mirrored address when the table is symmetric.
+  constexpr bool kMirror = LOG2N == 13;
+  const float* wlo = p.window + t;
+  const float* whi = (kMirror && p.win_mirror) ? p.window + (T - 1 - t) + 31 * T : p.window + t + 32 * T;
+  const int wstep = (kMirror && p.win_mirror) ? -T : T;
+  auto wtap = [&](int r) -> float {
+    if constexpr (kMirror) return r < 32 ? __ldg(wlo + T * r) : __ldg(whi + wstep * (r - 32));
+    else return __ldg(wlo + T * r);
+  };
 
   auto is_candidate = [&](uint32_t j) -> bool {          // process.cpp:46-53
     const uint32_t i = j ^ half;
@@ -143,10 +157,10 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     if constexpr (!kStaged) {
       const float2* src = reinterpret_cast<const float2*>(p.raw) + buf_index * N + t;
 #pragma unroll
-      for (int r = 0; r < 64; r++) v[r] = __ldg(src + T * r);
+      for (int r = 0; r < 64; r++) v[r] = ldg_stream(src + T * r);
 #pragma unroll
       for (int r = 0; r < 64; r++) {
-        const float w = __ldg(p.window + t + T * r);
+        const float w = wtap(r);
         v[r] = __fmul2_rn(v[r], make_float2(w, w));
       }
     } else {
@@ -169,7 +183,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
           bi = __byte_perm(x, kMagicBits, 0x7610);
           bq = __byte_perm(x, kMagicBits, 0x7632);
         }
-        const float w = __ldg(p.window + t + T * r);
+        const float w = wtap(r);
         v[r] = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(bi), __uint_as_float(bq)), negc), make_float2(w, w));
       }
     }
@@ -222,11 +236,15 @@ spectrum_sense_p64_kernel(const KernelParams p) {
       // ---- pass 2: 32 radix-2 butterflies j = t + 128 c: inputs j and j + 4096, twiddle W_8192^j ----------------
       const float2* base = tile + t + (t >> 6);
 #pragma unroll
-      for (int c = 0; c < 32; c++) {
-        const float2 a = base[GSTRIDE * c];
-        const float2 b = cmul(base[GSTRIDE * c + 4096 + 64], __ldg(twB + c * T + t));
-        v[c] = cadd(a, b);                             // bin t + 128 c
-        v[32 + c] = csub(a, b);                        // bin t + 128 (c + 32)
+      for (int c = 0; c < 16; c++) {
+        const float2 w = __ldg(twB + c * T + t);       // W_8192^(t + 128 c); row c + 16 is this times -i
+        const float2 a0 = base[GSTRIDE * c], a1 = base[GSTRIDE * (c + 16)];
+        const float2 b0 = cmul(base[GSTRIDE * c + 4096 + 64], w);
+        const float2 b1 = cmul(base[GSTRIDE * (c + 16) + 4096 + 64], w);
+        v[c] = cadd(a0, b0);                           // bin t + 128 c
+        v[32 + c] = csub(a0, b0);                      // bin t + 128 (c + 32)
+        v[16 + c] = add_mi(a1, b1);                    // bin t + 128 (c + 16)
+        v[48 + c] = sub_mi(a1, b1);                    // bin t + 128 (c + 48)
       }
     }
 

@@ -176,7 +176,7 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_cur) * N * 2) + lane;
 #pragma unroll
-    for (int r = 0; r < 32; r++) raw[r] = __ldg(src + 32 * r);
+    for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
   }
 #endif
 
@@ -226,7 +226,7 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     if (has_next) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_next) * N * 2) + lane;
 #pragma unroll
-      for (int r = 0; r < 32; r++) raw[r] = __ldg(src + 32 * r);
+      for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
     }
 #endif
 

@@ -41,9 +41,11 @@ def check_power(got_db, true_db64, ref32_db=None, acc_factor=2.5):
 
 
 def run_case(kind, n, enob, dc, K, n_spectra, seed, win_type=S.WIN_BLACKMAN_HARRIS, max_spectra=None,
-             hit_cap=0, acc_factor=2.5):
+             hit_cap=0, acc_factor=2.5, skew_window=False):
     raw = synth.make_buffers(kind, n, n_spectra * K, enob, seed)
     window = S.window_build(win_type, n)
+    if skew_window:      # a table that is NOT mirror symmetric (the ABI takes any table)
+        window = (window * np.linspace(0.8, 1.2, n)).astype(np.float32)
     use_w = S.use_window(0.75, n)
     truth = O.pipeline(raw, n, 8_000_000, enob, kind, dc, K, 0.0, window, use_w, precision=1, want_f64=True)
     thr = synth.guard_banded_threshold(truth["spectra_db64"], n, use_w)
@@ -101,6 +103,14 @@ def test_cfg3_int16_4096_avg64():
 
 def test_cfg4_fc32_8192_hann():
     run_case(S.KIND_FLOAT_COMPLEX, 8192, 0, False, 1, 17, seed=4000, win_type=S.WIN_HANN)
+
+
+@pytest.mark.parametrize("kind,enob,dc", [(S.KIND_BYTE_COMPLEX, 8, True), (S.KIND_SHORT_COMPLEX, 12, False),
+                                          (S.KIND_FLOAT_COMPLEX, 0, False)])
+@pytest.mark.parametrize("log2n", [11, 12, 13])
+def test_asymmetric_window_table(log2n, kind, enob, dc):
+    """The 64-points-per-thread kernels read mirrored taps only when the table is symmetric."""
+    run_case(kind, 1 << log2n, enob, dc, 1, 5, seed=6000 + log2n * 10 + kind, skew_window=True)
 
 
 def test_chunked_submit_and_hit_cap():
