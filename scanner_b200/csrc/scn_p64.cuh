@@ -144,6 +144,24 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     }
   }
 
+  // fp32 IQ, K = 1: the imaginary halves of v[] are dead once the powers are formed, so the first 32 points of the
+  // NEXT buffer are loaded into those 64 registers before the epilogue (dB, stores, detection) and their latency
+  // hides behind it; the other 32 points load at the top of the next tile as before.
+#ifndef SCN_P64_PREFETCH
+#define SCN_P64_PREFETCH 1
+#endif
+  constexpr bool kPrefetch = SCN_P64_PREFETCH && !kStaged && !AVG;
+#ifndef SCN_P64_PREFETCH_13
+#define SCN_P64_PREFETCH_13 16
+#endif
+  constexpr int kPre = !kPrefetch ? 0 : (LOG2N == 12 ? 32 : SCN_P64_PREFETCH_13);   // points prefetched
+  float2 nxt[kPrefetch ? kPre : 1];
+  if constexpr (kPrefetch) {
+    const float2* src = reinterpret_cast<const float2*>(p.raw) + size_t(s) * N + t;
+#pragma unroll
+    for (int r = 0; r < kPre; r++) nxt[r] = ldg_stream(src + T * r);
+  }
+
   float acc[AVG ? 64 : 1];
   while (true) {
     uint32_t ns = s, nk = k + 1;
@@ -157,7 +175,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     if constexpr (!kStaged) {
       const float2* src = reinterpret_cast<const float2*>(p.raw) + buf_index * N + t;
 #pragma unroll
-      for (int r = 0; r < 64; r++) v[r] = ldg_stream(src + T * r);
+      for (int r = 0; r < 64; r++) v[r] = (kPrefetch && r < kPre) ? nxt[r] : ldg_stream(src + T * r);
 #pragma unroll
       for (int r = 0; r < 64; r++) {
         const float w = wtap(r);
@@ -255,6 +273,13 @@ spectrum_sense_p64_kernel(const KernelParams p) {
       float pw = __fadd_rn(sq2.x, sq2.y);
       if constexpr (AVG) pw = acc[x] = (k == 0) ? pw : __fadd_rn(acc[x], pw);
       v[x].x = pw;
+    }
+    if constexpr (kPrefetch) {
+      if (has_next) {
+        const float2* src = reinterpret_cast<const float2*>(p.raw) + size_t(ns) * N + t;
+#pragma unroll
+        for (int r = 0; r < kPre; r++) nxt[r] = ldg_stream(src + T * r);
+      }
     }
 
     if (!epilogue_tile) {
