@@ -229,9 +229,23 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def calibrate_threshold_gpu(wl: dict, window: np.ndarray, use_w: int, device: int) -> float:
+    """Product arm: threshold = the 99.9th percentile of candidate-bin dB over a fixed-seed sample, taken from the
+    GPU path's own spectra (no oracle on this arm outside the cpu_baseline / parity-check legs), nudged away from
+    any sample bin (guard band): a few hits per spectrum, as a scanner would run."""
+    import scanner_b200 as S
+    from tests import synth
+    K = wl["K"]
+    raw = synth_host(wl, 16 * K, seed=77)
+    with S.SpectrumSense(wl["n"], wl["fs"], wl["enob"], 3.0e38, window, sample_kind=wl["kind"],
+                         correct_dc_offset=wl["dc"], averaging=K, max_spectra=16, flags=S.OUT_SPECTRUM,
+                         device=device) as ss:
+        db = ss.process(raw, want_hits=False)["spectra_db"].astype(np.float64)
+    return synth.guard_banded_threshold(db, wl["n"], use_w, quantile=0.999)
+
+
 def calibrate_threshold(wl: dict, window: np.ndarray, use_w: int) -> float:
-    """Threshold = the 99.9th percentile of candidate-bin dB over a fixed-seed sample (double oracle),
-    nudged away from any sample bin (guard band): a few hits per spectrum, as a scanner would run."""
+    """Reference arm: the same rule evaluated with the double-precision oracle."""
     import oracle as O
     from tests import synth
     K = wl["K"]
@@ -285,7 +299,7 @@ def main() -> None:
     n_steps = len(table)
     window = S.window_build(wl["win"], n)
     use_w = S.use_window(0.75, n)
-    thr = calibrate_threshold(wl, window, use_w)
+    thr = calibrate_threshold_gpu(wl, window, use_w, local_rank)
 
     # ---- shard: global units (spectra) in step-major order, contiguous range per rank ------------
     spectra_per_step_per_gpu = max(1, wl["buffers_per_step"] // K)
