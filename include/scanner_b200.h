@@ -183,6 +183,15 @@ SCN_API int scn_summarize_steps(scn_ctx* ctx, const uint32_t* d_hit_mask, const 
 SCN_API int scn_merge_step_records(scn_ctx* ctx, const uint32_t* d_parts, uint32_t n_parts,
                                    uint32_t n_steps, uint32_t* d_out, void* stream);
 
+/* ---- Standalone sample conversion (replaces Utility::*_to_float_complex, utility.cpp:9-84, as called by
+ * MessageQueue::AppendSamples, messageQueue.h:190-237) -------------------------------------------------
+ * raw: n_buffers buffers of the context's sample kind; out: n_buffers * sample_count fftwf_complex
+ * (interleaved float re, im), bit for bit what the reference stores in its queue messages and writes to its
+ * recording files (messageQueue.h:126-131): enob wrap, optional DC correction with the reference's
+ * unsigned division.  The fused kernel does not need this; the trigger/record path does. */
+SCN_API int scn_convert_device(scn_ctx* ctx, const void* d_raw, uint32_t n_buffers, float* d_out, void* stream);
+SCN_API int scn_convert_host(scn_ctx* ctx, const void* raw, uint32_t n_buffers, float* out);
+
 /* ---- HackRF sweep-frame pre-pass (replaces HackRFSource::interpolateSamples, hackRFSource.cpp:186-222) ----
  * d_transfers: n_transfers sweep-mode transfers of valid_length bytes each, int8 IQ, device
  * resident, patched IN PLACE exactly as the reference patches them (frame header 0x7F 0x7F + LE64

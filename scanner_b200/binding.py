@@ -73,6 +73,8 @@ SYMBOLS = [
     ("scn_summarize_steps", _I, [_VP, _VP, _VP, _U32, _U64, _U32, _U32, _VP, _VP]),
     ("scn_merge_step_records", _I, [_VP, _VP, _U32, _U32, _VP, _VP]),
     ("scn_hackrf_prepass_device", _I, [_VP, _VP, _U32, _U32, _VP, _VP, _VP]),
+    ("scn_convert_device", _I, [_VP, _VP, _U32, _VP, _VP]),
+    ("scn_convert_host", _I, [_VP, _VP, _U32, _VP]),
     ("scn_use_window", _U32, [_D, _U32]),
     ("scn_hit_frequency", _U64, [_D, _U32, _U32, _U32]),
     ("scn_frequency_table", _U32, [_U32, _D, _D, _D, _D, C.POINTER(_D), _U32]),
@@ -274,6 +276,17 @@ class SpectrumSense:
     def merge_step_records(self, d_parts: int, n_parts: int, n_steps: int, d_out: int, stream: int = 0) -> None:
         _check(self._lib.scn_merge_step_records(self._ctx, _VP(d_parts), n_parts, n_steps, _VP(d_out),
                                                 _VP(stream or None)))
+
+    def convert(self, raw: np.ndarray) -> np.ndarray:
+        """raw buffers -> complex64 [n_buffers][N], the reference's converters (utility.cpp:9-84) on the GPU."""
+        raw = np.ascontiguousarray(raw)
+        nb = raw.nbytes // self.buffer_bytes
+        out = np.empty((nb, self.N), np.complex64)
+        _check(self._lib.scn_convert_host(self._ctx, _ptr(raw), nb, _ptr(out)))
+        return out
+
+    def convert_device(self, d_raw: int, n_buffers: int, d_out: int, stream: int = 0) -> None:
+        _check(self._lib.scn_convert_device(self._ctx, _VP(d_raw), n_buffers, _VP(d_out), _VP(stream or None)))
 
     def hackrf_prepass_device(self, d_transfers: int, n_transfers: int, valid_length: int,
                               d_frequency_hz: int = 0, d_status: int = 0, stream: int = 0) -> None:

@@ -20,6 +20,8 @@ namespace scn {
 cudaError_t launch_summarize(const uint32_t* masks, const uint32_t* counts, uint32_t n_spectra,
                              uint64_t first_unit, uint32_t units_per_step, uint32_t n_steps, uint32_t words,
                              uint32_t* records, int num_sms, cudaStream_t stream);
+cudaError_t launch_convert(int kind, const void* raw, float* out, uint32_t n, uint32_t n_buffers, float onebymax,
+                           bool correct_dc, int num_sms, cudaStream_t stream);
 cudaError_t launch_hackrf_prepass(void* transfers, uint32_t n_transfers, uint32_t valid_length,
                                   uint64_t* frequency_hz, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_merge(const uint32_t* parts, uint32_t n_parts, uint32_t n_steps, uint32_t rec_words,
@@ -119,6 +121,10 @@ struct scn_ctx {
   std::vector<Slot> slots;
   uint32_t next_slot = 0;
   uint64_t launches = 0;
+  // scn_convert_host staging (grown on demand)
+  void* d_conv_raw = nullptr;
+  float* d_conv_out = nullptr;
+  uint32_t conv_capacity = 0;
 };
 
 namespace {
@@ -495,6 +501,8 @@ SCN_API int scn_destroy(scn_ctx* c) {
   if (c->d_y) cudaFree(c->d_y);
   if (c->d_p) cudaFree(c->d_p);
   if (c->d_dcs) cudaFree(c->d_dcs);
+  if (c->d_conv_raw) cudaFree(c->d_conv_raw);
+  if (c->d_conv_out) cudaFree(c->d_conv_out);
   delete c;
   return SCN_OK;
 }
@@ -681,6 +689,35 @@ SCN_API int scn_merge_step_records(scn_ctx* c, const uint32_t* d_parts, uint32_t
   SCN_CUDA(cudaSetDevice(c->cfg.device));
   SCN_CUDA(scn::launch_merge(d_parts, n_parts, n_steps, c->words + 2, d_out, static_cast<cudaStream_t>(stream)));
   c->launches++;
+  return SCN_OK;
+}
+
+SCN_API int scn_convert_device(scn_ctx* c, const void* d_raw, uint32_t n_buffers, float* d_out, void* stream) {
+  if (!c || (n_buffers && (!d_raw || !d_out))) return fail(SCN_ERR_INVALID, "convert: bad arguments");
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  SCN_CUDA(scn::launch_convert(int(c->cfg.sample_kind), d_raw, d_out, c->cfg.sample_count, n_buffers, c->onebymax,
+                               c->cfg.correct_dc_offset != 0, c->num_sms, static_cast<cudaStream_t>(stream)));
+  if (n_buffers) c->launches++;
+  return SCN_OK;
+}
+
+SCN_API int scn_convert_host(scn_ctx* c, const void* raw, uint32_t n_buffers, float* out) {
+  if (!c || (n_buffers && (!raw || !out))) return fail(SCN_ERR_INVALID, "convert: bad arguments");
+  if (n_buffers == 0) return SCN_OK;
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  const size_t N = c->cfg.sample_count;
+  if (n_buffers > c->conv_capacity) {
+    if (c->d_conv_raw) cudaFree(c->d_conv_raw);
+    if (c->d_conv_out) cudaFree(c->d_conv_out);
+    c->d_conv_raw = nullptr; c->d_conv_out = nullptr; c->conv_capacity = 0;
+    SCN_CUDA(cudaMalloc(&c->d_conv_raw, size_t(n_buffers) * c->buf_bytes));
+    SCN_CUDA(cudaMalloc(&c->d_conv_out, size_t(n_buffers) * N * 2 * sizeof(float)));
+    c->conv_capacity = n_buffers;
+  }
+  SCN_CUDA(cudaMemcpy(c->d_conv_raw, raw, size_t(n_buffers) * c->buf_bytes, cudaMemcpyHostToDevice));
+  int rc = scn_convert_device(c, c->d_conv_raw, n_buffers, c->d_conv_out, nullptr);
+  if (rc != SCN_OK) return rc;
+  SCN_CUDA(cudaMemcpy(out, c->d_conv_out, size_t(n_buffers) * N * 2 * sizeof(float), cudaMemcpyDeviceToHost));
   return SCN_OK;
 }
 
