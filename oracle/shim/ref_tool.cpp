@@ -11,6 +11,12 @@
 //        producer thread and runs ProcessSamples::StartProcessing (process.cpp:316) with ONE worker
 //        (the reference's two workers race on the shared FFT object, fft.cpp:20-25);
 //        stdout is the reference's own output ("Start scan at ...", "freq %lu power_db %f", ...).
+//   ref_tool record <kind> <N> <fs> <enob> <dc> <threshold> <win_type> <buffers_per_sweep> <raw_file> <freq_file>
+//                   <file_base> <pre_trigger> <post_trigger>
+//        like scan (frequency domain, one worker) with triggered recording on: SampleQueue(doWrite = true) and
+//        ProcessSamples(fileNameBase, preTrigger, postTrigger); the reference's writer thread
+//        (messageQueue.h:98-139) produces the files.  SetIsDone is held back until the queue has drained,
+//        because the reference's writer stops at SetIsDone (messageQueue.h:100-124).
 //   ref_tool hackrf_prepass <N> <fs> <start> <stop> <valid_length> <in_file> <out_file>
 //        runs HackRFSource::interpolateSamples (hackRFSource.cpp:186-222) on every transfer of
 //        <in_file>; <out_file> = per transfer { double returned centre frequency, patched bytes };
@@ -36,7 +42,9 @@
 #include <mutex>
 #include <condition_variable>
 #include "fft.h"
+#define private public   // ref_tool polls MessageQueue::IsEmpty() (access only; the header is unmodified)
 #include "messageQueue.h"
+#undef private
 #include "signalSource.h"
 #include "process.h"
 #define class struct   // interpolateSamples is a private member of `class HackRFSource` (access only; the source is unmodified)
@@ -139,6 +147,50 @@ int main(int argc, char** argv) {
     producer.join();
     fflush(stdout);
     return 0;
+  }
+  if (cmd == "record" && argc == 15) {
+    int kind = atoi(argv[2]);
+    uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    bool dc = atoi(argv[6]) != 0;
+    float threshold = float(atof(argv[7]));
+    int win = atoi(argv[8]);
+    uint32_t per_sweep = atoi(argv[9]);
+    std::vector<char> raw = read_file(argv[10]);
+    std::vector<char> fr = read_file(argv[11]);
+    std::string base = argv[12];
+    uint32_t pre = atoi(argv[13]), post = atoi(argv[14]);
+    const double* freqs = reinterpret_cast<const double*>(fr.data());
+    size_t bb = n * bytes_per_sample(kind);
+    size_t nbuf = raw.size() / bb;
+    {
+      ProcessSamples process(n, fs, enob, threshold, gr::fft::window::win_type(win), ProcessSamples::FrequencyDomain, 1,
+                             base, 0.75, 0.0, pre, post);
+      SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, true);
+      std::thread producer([&]() {
+        for (size_t b = 0; b < nbuf; b++) {
+          char* p = raw.data() + b * bb;
+          time_t tm = (per_sweep && (b % per_sweep) == 0) ? time_t(1000000000 + b) : 0;
+          if (kind == SampleQueue::ByteComplex)
+            queue.AppendSamples(reinterpret_cast<int8_t(*)[2]>(p), freqs[b], tm);
+          else if (kind == SampleQueue::ShortComplex)
+            queue.AppendSamples(reinterpret_cast<int16_t(*)[2]>(p), freqs[b], tm);
+          else if (kind == SampleQueue::Short)
+            queue.AppendSamples(reinterpret_cast<int16_t*>(p), reinterpret_cast<int16_t*>(p) + n, freqs[b], tm);
+          else
+            queue.AppendSamples(reinterpret_cast<fftwf_complex*>(p), freqs[b], tm);
+          usleep(2000);                    // a live source's pace: the writer thread is back in its wait between triggers
+        }
+        while (!queue.IsEmpty()) usleep(1000);
+        usleep(300000);                    // last message processed, writer caught up
+        queue.SetIsDone();
+      });
+      process.StartProcessing(queue);
+      producer.join();
+      fflush(stdout);
+      // every window was closed by the writer (messageQueue.h:132-135).  ~MessageQueue would fclose the last
+      // FILE* a second time (messageQueue.h:186-188: m_writeFile is never reset) and abort in glibc, so leave here.
+      _exit(0);
+    }
   }
   if (cmd == "hackrf_prepass" && argc == 9) {
     uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));

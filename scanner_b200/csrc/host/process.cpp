@@ -30,7 +30,9 @@ ProcessSamples::ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_
   if (scn_window_build(windowType, numSamples, m_window.data()) != SCN_OK) Die("FFTWindow");
 }
 
-ProcessSamples::~ProcessSamples() {}
+ProcessSamples::~ProcessSamples() {
+  if (m_writeCtx) scn_destroy(m_writeCtx);
+}
 
 // Hit records per spectrum copied back with every batch; a spectrum with more hits than this is re-run
 // alone through a full-capacity context (rare: the reference itself treats > 1047 hits as an event,
@@ -69,8 +71,7 @@ void ProcessSamples::TimeToString(time_t t, char* buffer, uint32_t length) {
 }
 
 void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t sequenceId) {
-  // Trigger/record bookkeeping of process.cpp:250-270.  The recording itself (file I/O) is out of
-  // scope; the window of sequence ids that WOULD be recorded is still tracked and forwarded.
+  // Trigger/record bookkeeping of process.cpp:250-270; the queue's writer thread records the window.
   if (m_writing) {
     if (doWrite) {
       uint64_t end = sequenceId + m_postTrigger + 1, cur = m_endSequenceId;
@@ -80,9 +81,9 @@ void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t
       m_writing = false;
     }
   } else if (doWrite && !m_fileNameBase.empty()) {
-    char name[320], tbuf[64];
-    TimeToString(time(nullptr), tbuf, sizeof(tbuf));
-    snprintf(name, sizeof(name), "%s%s-%.0f", m_fileNameBase.c_str(), tbuf, centerFrequency);
+    char name[320], tbuf[64];                       // process.cpp:160-181: base + time + "-<frequency>-<counter>"
+    TimeToString(m_clock ? m_clock() : time(nullptr), tbuf, sizeof(tbuf));
+    snprintf(name, sizeof(name), "%s%s-%.0f-%u", m_fileNameBase.c_str(), tbuf, centerFrequency, ++m_fileCounter);
     const uint64_t dec = sequenceId < m_preTrigger ? sequenceId : m_preTrigger;
     m_sampleQueue->BeginWrite(sequenceId - dec, name);
     m_writing = true;
@@ -117,6 +118,9 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * cap : 0);
   std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
 
+  bool processedAny = false;
+  uint64_t lastSequenceId = 0;
+  double lastFrequency = 0.0;
   auto finish = [&](InFlight& f) {
     const uint32_t nSpectra = f.nSpectra;
     if (nSpectra) {
@@ -173,6 +177,9 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
           q->SendAck();                                   // process.cpp:303-307
         }
         ProcessWrite(doWrite, header.m_frequency, header.m_sequenceId);
+        processedAny = true;
+        lastSequenceId = header.m_sequenceId;
+        lastFrequency = header.m_frequency;
       }
     }
     for (auto* m : f.batch) q->MessageProcessed(m);       // process.cpp:309
@@ -214,6 +221,12 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
       cur ^= 1;
     }
   }
+  if (processedAny) {
+    // "Shutdown writing gracefully" (process.cpp:311-313): a window that ends at or before the last message closes
+    uint64_t cur = m_endSequenceId;
+    while (cur < lastSequenceId && !m_endSequenceId.compare_exchange_weak(cur, lastSequenceId)) {}
+    ProcessWrite(false, lastFrequency, lastSequenceId);
+  }
   for (auto& s : slot) scn_free_pinned(s.staging);
   if (fullCtx) scn_destroy(fullCtx);
   scn_destroy(ctx);
@@ -221,6 +234,15 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
 
 bool ProcessSamples::StartProcessing(SampleQueue& sampleQueue) {
   m_sampleQueue = &sampleQueue;
+  if (!m_fileNameBase.empty() && sampleQueue.m_kind != SampleQueue::FloatComplex && !m_writeCtx) {
+    // recording writes fftwf_complex (messageQueue.h:127-130); the queue holds raw samples, so its writer thread
+    // converts each recorded message with the reference's converter arithmetic on the GPU
+    m_writeCtx = CreateContext(sampleQueue.m_kind, sampleQueue.GetEnob(), sampleQueue.GetCorrectDCOffset(), 1, 1);
+    scn_ctx* ctx = m_writeCtx;
+    sampleQueue.SetWriteConverter([ctx](const void* raw, uint32_t nBuffers, float* out) {
+      return scn_convert_host(ctx, raw, nBuffers, out) == SCN_OK;
+    });
+  }
   for (uint32_t t = 0; t < m_threadCount; t++) {
     if (m_out) fprintf(m_out, "Starting process thread %u\n", t);
     m_threads[t] = new std::thread(&ProcessSamples::ThreadWorker, this, t);

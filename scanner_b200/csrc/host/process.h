@@ -82,4 +82,9 @@ class ProcessSamples {
   std::atomic<uint64_t> m_buffersProcessed{0}, m_hitCount{0}, m_launches{0};
   std::atomic<bool> m_writing{false};
   std::atomic<uint64_t> m_endSequenceId{0};
+  uint32_t m_fileCounter = 0;                      // process.cpp:169
+  scn_ctx* m_writeCtx = nullptr;                   // converts recorded messages (scn_convert_host), writer thread only
+  std::function<time_t()> m_clock;                 // file-name stamps; default time(NULL)
+ public:
+  void SetClock(std::function<time_t()> clock) { m_clock = std::move(clock); }   // reproducible replays
 };

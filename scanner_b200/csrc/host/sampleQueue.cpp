@@ -21,7 +21,8 @@ SampleQueue::SampleQueue(SampleKind kind, uint32_t enob, uint32_t sampleCount, u
                          bool correctDCOffset, bool doWrite)
     : m_kind(kind), m_enob(enob), m_sampleCount(sampleCount), m_bufferCount(bufferCount),
       m_correctDCOffset(correctDCOffset), m_doWrite(doWrite),
-      m_bufferBytes(size_t(sampleCount) * BytesPerSample(kind)) {
+      m_bufferBytes(size_t(sampleCount) * BytesPerSample(kind)),
+      m_writeCapacity(bufferCount / 10 ? bufferCount / 10 : 1) {      // messageQueue.h:149
   assert(kind > Illegal && kind <= FloatComplex);
   // like the reference's pool: 10 % more messages than queue slots (messageQueue.h:150)
   const uint32_t poolCount = uint32_t(bufferCount * 1.1) + 1;
@@ -38,9 +39,22 @@ SampleQueue::SampleQueue(SampleKind kind, uint32_t enob, uint32_t sampleCount, u
     m.m_header = MessageHeader{MessageHeader::Free, 0, 0.0, 0, 0};
     m_free.push_back(&m);
   }
+  if (doWrite) {
+    printf("Starting write thread...\n");                            // messageQueue.h:164-168
+    m_writeThread.reset(new std::thread(&SampleQueue::WriteThreadWorker, this));
+  }
 }
 
 SampleQueue::~SampleQueue() {
+  if (m_writeThread) {
+    printf("Stopping write thread...\n");                            // messageQueue.h:175-178
+    {
+      std::unique_lock<std::mutex> lock(m_writeMutex);
+      m_writeShutdown = true;
+      m_conditionWrite.notify_all();
+    }
+    m_writeThread->join();
+  }
   if (m_slab) {
     scn_free_pinned(m_slab);
   } else {
@@ -141,20 +155,96 @@ uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxC
 
 void SampleQueue::MessageProcessed(MessageType* message) {
   assert(message->m_header.m_kind != MessageHeader::Illegal);
-  // The reference parks processed messages in a write-history ring for triggered recording
-  // (messageQueue.h:259-273); recording is out of scope here, so the message returns to the pool.
-  Free(message);
+  if (!m_doWrite) {            // no recording: nothing will ever read the history, the message returns to the pool
+    Free(message);
+    return;
+  }
+  // messageQueue.h:259-273: park the message in the write history, evicting the oldest
+  std::unique_lock<std::mutex> lock(m_writeMutex);
+  m_writeBuffer[message->m_header.m_sequenceId] = message;
+  TrimWriteHistory();
+  m_conditionWrite.notify_all();
+}
+
+void SampleQueue::TrimWriteHistory() {
+  // the history holds bufferCount/10 messages (messageQueue.h:149,264-269) -- plus whatever an open window has
+  // not written yet: the pool (and with it the producer) absorbs a writer that falls behind
+  while (m_writeBuffer.size() > m_writeCapacity) {
+    auto oldest = m_writeBuffer.begin();
+    if (!m_writeJobs.empty() && oldest->first >= m_writeJobs.front().cursor) break;
+    m_evictedBelow = oldest->first + 1;
+    Free(oldest->second);
+    m_writeBuffer.erase(oldest);
+  }
+}
+
+void SampleQueue::SetWriteConverter(Converter convert) {
+  std::unique_lock<std::mutex> lock(m_writeMutex);
+  m_convert = convert;
 }
 
 void SampleQueue::BeginWrite(uint64_t startSequenceId, std::string fileName) {
-  printf("BeginWrite %s: %lu\n", fileName.c_str(), (unsigned long)startSequenceId);
+  printf("BeginWrite %s: %lu\n", fileName.c_str(), (unsigned long)startSequenceId);   // messageQueue.h:275-282
+  std::unique_lock<std::mutex> lock(m_writeMutex);
   m_writeStartSequenceId = startSequenceId;
   m_writeEndSequenceId = UINT64_MAX;
+  if (!m_doWrite) return;
+  FILE* f = fopen(fileName.c_str(), "w");
+  if (!f) { perror(fileName.c_str()); exit(1); }
+  m_writeJobs.push_back(WriteJob{startSequenceId, UINT64_MAX, f});
+  m_conditionWrite.notify_all();
 }
 
 void SampleQueue::EndWrite(uint64_t sequenceId) {
-  printf("EndWrite %lu\n", (unsigned long)sequenceId);
+  printf("EndWrite %lu\n", (unsigned long)sequenceId);                                  // messageQueue.h:284-288
+  std::unique_lock<std::mutex> lock(m_writeMutex);
   m_writeEndSequenceId = sequenceId;
+  if (!m_writeJobs.empty()) m_writeJobs.back().end = sequenceId;
+  m_conditionWrite.notify_all();
+}
+
+void SampleQueue::WriteThreadWorker() {
+  std::unique_lock<std::mutex> lock(m_writeMutex);
+  while (true) {
+    m_conditionWrite.wait(lock, [this] { return !m_writeJobs.empty() || m_writeShutdown; });
+    if (m_writeJobs.empty()) break;
+    WriteJob& job = m_writeJobs.front();                  // (push_back does not invalidate a deque reference)
+    uint64_t& seq = job.cursor;
+    while (true) {
+      // next message of the window: the exact id once it has been processed; an id the history no longer holds
+      // is skipped; at shutdown whatever is still parked is flushed
+      m_conditionWrite.wait(lock, [&] {
+        if (seq < m_evictedBelow) seq = m_evictedBelow;
+        return seq >= job.end || m_writeBuffer.count(seq) != 0 || m_writeShutdown;
+      });
+      if (seq >= job.end) break;
+      auto it = m_writeBuffer.find(seq);
+      if (it == m_writeBuffer.end()) {                    // shutting down: jump to the next parked id, if any
+        it = m_writeBuffer.lower_bound(seq);
+        if (it == m_writeBuffer.end() || it->first >= job.end) break;
+        seq = it->first;
+      }
+      MessageType* message = it->second;
+      printf("Writing %lu\n", (unsigned long)seq);                                       // messageQueue.h:125
+      const void* data = message->m_data;
+      if (m_kind != FloatComplex) {
+        if (!m_convert) { fprintf(stderr, "SampleQueue: recording needs a converter (SetWriteConverter)\n"); exit(1); }
+        m_writeScratch.resize(size_t(m_sampleCount) * 2);
+        if (!m_convert(message->m_data, 1, m_writeScratch.data())) {
+          fprintf(stderr, "SampleQueue: sample conversion failed: %s\n", scn_last_error());
+          exit(1);
+        }
+        data = m_writeScratch.data();
+      }
+      fwrite(data, sizeof(fftwf_complex), m_sampleCount, job.file);                       // messageQueue.h:127-130
+      m_written++;
+      seq++;
+      TrimWriteHistory();
+    }
+    fclose(job.file);
+    m_writeJobs.pop_front();
+    TrimWriteHistory();
+  }
 }
 
 void SampleQueue::SetIsDone() {

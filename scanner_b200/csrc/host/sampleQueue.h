@@ -12,14 +12,24 @@
 //     unless SetDropFirstSweep(false);
 //   * sequence ids count accepted buffers; FIFO delivery; bounded: Append blocks when full.
 // GetNextBatch() is the batched form of GetNextSamples() the GPU consumer uses.
-// The triggered-recording writer thread (messageQueue.h:98-139) is out of scope (disk I/O):
-// BeginWrite/EndWrite only keep the requested window.
+// Triggered recording (messageQueue.h:98-139, 259-288): with doWrite the queue parks processed messages in a
+// history of bufferCount/10 and a writer thread writes the window [BeginWrite start, EndWrite id) to the named
+// file as fftwf_complex, exactly the bytes the reference writes.  The messages hold RAW samples here, so the
+// writer converts through the callback ProcessSamples installs (scn_convert_host: the reference's converters
+// on the GPU); there is no CPU converter in this library.  Unlike the reference's writer -- which can miss a
+// BeginWrite wake-up, stops at SetIsDone with messages unwritten and waits forever for an evicted start --
+// this one writes strictly in sequence order whatever order workers finish in, keeps what an open window
+// still needs out of the history's eviction, skips what had already left it, and flushes at shutdown; where the reference's races do not bite, the files are identical.
 #pragma once
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <ctime>
 #include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -74,6 +84,10 @@ class SampleQueue {
 
   void BeginWrite(uint64_t startSequenceId, std::string fileName);
   void EndWrite(uint64_t sequenceId);
+  // raw buffers of this queue's kind -> interleaved float re/im; false == failure (the writer then exits(1))
+  typedef std::function<bool(const void* raw, uint32_t nBuffers, float* out)> Converter;
+  void SetWriteConverter(Converter convert);
+  uint64_t GetWrittenCount() const { return m_written; }
   void SetIsDone();
   bool GetIsDone();
   bool ReceivedAck();
@@ -107,6 +121,22 @@ class SampleQueue {
   bool m_done = false;
   std::atomic<bool> m_acknowledged{true};
   uint64_t m_writeStartSequenceId = 0, m_writeEndSequenceId = 0;
+
+  // recording
+  void WriteThreadWorker();
+  std::mutex m_writeMutex;
+  std::condition_variable m_conditionWrite;
+  std::map<uint64_t, MessageType*> m_writeBuffer;      // processed messages by sequence id (history)
+  uint32_t m_writeCapacity;
+  uint64_t m_evictedBelow = 0;                          // every id below this has left the history
+  std::unique_ptr<std::thread> m_writeThread;
+  struct WriteJob { uint64_t cursor, end; FILE* file; };  // one per BeginWrite, written in order, each to completion
+  void TrimWriteHistory();                               // caller holds m_writeMutex
+  std::deque<WriteJob> m_writeJobs;
+  bool m_writeShutdown = false;
+  Converter m_convert;
+  std::vector<float> m_writeScratch;
+  uint64_t m_written = 0;
 
   std::mutex m_mutex;
   std::condition_variable m_conditionEmpty, m_conditionFull;

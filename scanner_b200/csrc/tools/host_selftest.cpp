@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unistd.h>
 #include <thread>
 #include <vector>
 
@@ -201,6 +202,62 @@ int main(int argc, char** argv) {
     CHECK(sb.GetNextSamples(&v, f, 3) == 2 && v.seq == 3 * N && f[0] == 103.0);
     CHECK(sb.GetNextSamples(&v, f, 3) == 0);
   }
+  // ---- triggered recording (messageQueue.h:98-139, 259-288) on fc32 messages (no conversion, no GPU)
+  {
+    const uint32_t N = 256;
+    char path[] = "/tmp/scn_selftest_rec_XXXXXX";
+    int fd = mkstemp(path);
+    CHECK(fd >= 0);
+    close(fd);
+    std::vector<float> buf(2 * N);
+    {
+      SampleQueue q(SampleQueue::FloatComplex, 0, N, 40, false, true);     // history = 4 messages
+      q.SetDropFirstSweep(false);
+      for (int b = 0; b < 12; b++) {
+        for (uint32_t i = 0; i < 2 * N; i++) buf[i] = float(b * 1000 + int(i));
+        q.AppendSamples(reinterpret_cast<fftwf_complex*>(buf.data()), 1e6, 0);
+      }
+      q.SetIsDone();
+      std::vector<SampleQueue::MessageType*> held;
+      for (int b = 0; b < 12; b++) {
+        SampleQueue::MessageType* m = q.GetNextSamples();
+        CHECK(m != nullptr && m->GetHeader().m_sequenceId == uint64_t(b));
+        if (b == 5) q.BeginWrite(3, path);                                   // trigger at 5, pre-trigger 2
+        if (b == 9) q.EndWrite(9);
+        // workers may finish out of order: 6 is parked after 7
+        if (b == 6) { held.push_back(m); continue; }
+        q.MessageProcessed(m);
+        if (b == 7) { q.MessageProcessed(held[0]); held.clear(); }
+      }
+      CHECK(q.GetNextSamples() == nullptr);
+    }                                                                        // destructor joins the writer
+    std::vector<char> rec = ReadAll(path);
+    CHECK(rec.size() == size_t(6) * N * 8);                                  // messages 3..8
+    const float* f = reinterpret_cast<const float*>(rec.data());
+    for (int k = 0; k < 6; k++) CHECK(f[size_t(k) * 2 * N + 7] == float((3 + k) * 1000 + 7));
+    // a start that has already left the history is skipped forward, and an open window is flushed at shutdown
+    {
+      SampleQueue q(SampleQueue::FloatComplex, 0, N, 20, false, true);     // history = 2 messages
+      q.SetDropFirstSweep(false);
+      for (int b = 0; b < 8; b++) {
+        for (uint32_t i = 0; i < 2 * N; i++) buf[i] = float(b * 1000 + int(i));
+        q.AppendSamples(reinterpret_cast<fftwf_complex*>(buf.data()), 1e6, 0);
+      }
+      q.SetIsDone();
+      for (int b = 0; b < 8; b++) {
+        SampleQueue::MessageType* m = q.GetNextSamples();
+        if (b == 6) q.BeginWrite(1, path);                                   // 1..3 are gone: history holds 4, 5
+        q.MessageProcessed(m);
+      }
+    }
+    rec = ReadAll(path);
+    CHECK(rec.size() == size_t(4) * N * 8);                                  // 4, 5, 6, 7
+    f = reinterpret_cast<const float*>(rec.data());
+    CHECK(f[3] == 4003.0f && f[size_t(3) * 2 * N + 3] == 7003.0f);
+    // integer kinds without a converter must not write garbage: covered by the GPU tests (SetWriteConverter)
+    remove(path);
+  }
+
   printf("host_selftest ok\n");
   return 0;
 }

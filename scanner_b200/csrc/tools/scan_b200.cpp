@@ -8,6 +8,10 @@
 //   scan_b200 synth <kind> <N> <fs> <enob> <dc> <threshold> <start> <stop> <buffers_per_step>
 //                   <iterations> <seed> [threads] [averaging]
 //       seeded SyntheticSource sweep (first sweep dropped like the reference: needs iterations >= 2).
+//   scan_b200 record <kind> <N> <fs> <enob> <dc> <threshold> <win_type> <buffers_per_sweep> <raw_file> <freq_file>
+//                    <file_base> <pre_trigger> <post_trigger> [threads]
+//       same arguments as oracle/_ref/ref_tool record: triggered recording on (SampleQueue doWrite, ProcessSamples
+//       fileNameBase / preTrigger / postTrigger); file-name stamps 1500000000 + 1000 k like ref_tool's clock.
 //   scan_b200 hackrf <N> <fs> <start> <stop> <threshold> <iterations> <valid_length> <stream_file> [threads]
 //       same arguments and capture file as oracle/_ref/ref_tool hackrf_scan: HackRFSweepSource replays the
 //       sweep-mode transfers with scan.cpp:177-188's settings (enob 8, DC correction on, ByteComplex).
@@ -101,6 +105,35 @@ int main(int argc, char** argv) {
     source.StartStreaming(1, queue);
     process.StartProcessing(queue);
     source.Join();
+    fflush(stdout);
+    return 0;
+  }
+  if (cmd == "record" && argc >= 15) {
+    const int kind = atoi(argv[2]);
+    const uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    const bool dc = atoi(argv[6]) != 0;
+    const float thr = float(atof(argv[7]));
+    const int win = atoi(argv[8]);
+    const uint32_t perSweep = atoi(argv[9]);
+    std::vector<char> raw = ReadFile(argv[10]);
+    std::vector<char> fr = ReadFile(argv[11]);
+    const std::string base = argv[12];
+    const uint32_t pre = atoi(argv[13]), post = atoi(argv[14]);
+    const uint32_t threads = argc > 15 ? atoi(argv[15]) : 1;
+    const size_t bb = SyntheticSource::BufferBytes(SampleQueue::SampleKind(kind), n);
+    const size_t nbuf = raw.size() / bb;
+    const double* freqs = reinterpret_cast<const double*>(fr.data());
+    ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs, nbuf, perSweep, fs, n);
+    ProcessSamples process(n, fs, enob, thr, win, ProcessSamples::FrequencyDomain, threads, base, 0.75, 0.0, pre, post);
+    uint64_t stamps = 0;
+    process.SetClock([&stamps]() { return time_t(1500000000 + 1000 * stamps++); });
+    {
+      SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, true);
+      source.Start();
+      source.StartStreaming(1, queue);
+      process.StartProcessing(queue);
+      source.Join();
+    }                                                           // ~SampleQueue flushes and joins the writer
     fflush(stdout);
     return 0;
   }
