@@ -186,6 +186,31 @@ def cpu_baseline(wl: dict, window: np.ndarray, threshold: float, use_w: int, tar
                       f"process.cpp:272-310 incl. the reference's per-buffer copies, one FFT plan per thread"}, sec
 
 
+def cpu_fft_upper_bound(wl: dict, target_s: float = 3.0):
+    """FFT-ONLY throughput of a tuned CPU library (scipy's pocketfft, complex64, all cores) on the workload's size:
+    an upper bound for what the reference's FFTW plan could reach on this host -- the oracle's own radix FFT stands
+    in for FFTW in `cpu_baseline`, and the reference's convert / window / dB / detect stages are NOT in this number
+    (SURVEY.md section 8d)."""
+    try:
+        import scipy.fft as sfft
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": str(e)}
+    n, nb = wl["n"], max(64, (32 << 20) // (wl["n"] * 8))
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((nb, n)) + 1j * rng.standard_normal((nb, n))).astype(np.complex64)
+    workers = os.cpu_count() or 1
+    sfft.fft(x, axis=1, workers=workers)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < target_s:
+        y = sfft.fft(x, axis=1, workers=workers)
+        reps += 1
+    sec = time.perf_counter() - t0
+    assert y.dtype == np.complex64
+    return {"value": nb * n * reps / sec / 1e6, "unit": UNIT, "cores": workers, "library": "scipy.fft (pocketfft) complex64",
+            "sample": f"{nb} x {n}-point forward FFTs x {reps} repeats ({sec:.1f} s), FFT only"}
+
+
 def run_reference(args) -> None:
     """Reference arm: the reference's own CPU algorithm (oracle restatement; the reference binary cannot
     be built here -- FFTW3/VOLK/gr-fft/Boost absent) on all host cores."""
@@ -520,10 +545,12 @@ def main() -> None:
     if rank == 0:
         cpu = None
         cpu2 = None
+        cpu_fft = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_baseline(wl, window, thr, use_w, args.cpu_seconds)
             # the reference itself runs exactly two worker threads (scan.cpp:217)
             cpu2, _ = cpu_baseline(wl, window, thr, use_w, min(args.cpu_seconds, 4.0), threads=2)
+            cpu_fft = cpu_fft_upper_bound(wl)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -536,7 +563,8 @@ def main() -> None:
                                    "per-step records" if world > 1 else "single GPU",
                        "threshold_db": thr, "spectrum_written": spectrum},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "cpu_baseline_2_threads": cpu2, "parity": parity, "step_ms": step_ms,
+            "cpu_baseline": cpu, "cpu_baseline_2_threads": cpu2, "cpu_fft_only_upper_bound": cpu_fft,
+            "parity": parity, "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
