@@ -18,3 +18,29 @@ for kind, n, enob, dc, K in cases:
 raw = synth.make_buffers(1, 4096, 6, 8, seed=3)
 with S.SpectrumSense(4096, 8_000_000, 8, -5.0, None, sample_kind=1, correct_dc_offset=True, mode=S.MODE_TIME_DOMAIN, max_spectra=6) as ss:
     print("time domain", ss.process(raw)["hit_count"].tolist())
+# fp32 K = 1 at N = 4096 (next-buffer prefetch into the dead imaginary registers) and an asymmetric window at N = 8192
+for n, skew in [(4096, False), (8192, True)]:
+    raw = synth.make_buffers(4, n, 7, 0, seed=n)
+    w = S.window_build(5, n)
+    if skew:
+        w = (w * np.linspace(0.8, 1.2, n)).astype(np.float32)
+    with S.SpectrumSense(n, 8_000_000, 0, 8.0, w, sample_kind=4, max_spectra=7, max_hits_per_spectrum=64) as ss:
+        print(ss.kernel_name, "skew" if skew else "", int(ss.process(raw)["hit_count"].sum()), flush=True)
+# standalone converters (every kind, DC on) and the HackRF sweep-frame pre-pass
+import torch
+for kind, enob in [(1, 8), (3, 12), (2, 12), (4, 0)]:
+    raw = synth.make_buffers(kind, 1024, 9, enob, seed=40 + kind)
+    with S.SpectrumSense(1024, 8_000_000, enob, 8.0, S.window_build(5, 1024), sample_kind=kind,
+                         correct_dc_offset=kind != 4) as ss:
+        print("convert kind", kind, float(np.abs(ss.convert(raw)).max()), flush=True)
+stream = np.zeros((5, 65536), np.uint8)
+stream[:, 0:2] = 0x7F
+stream[:, 2] = np.arange(5)
+stream[1, 10:12] = 0x7F
+with S.SpectrumSense(1024, 8_000_000, 8, 8.0, S.window_build(5, 1024), sample_kind=1, correct_dc_offset=True) as ss:
+    d = torch.from_numpy(stream).cuda()
+    f = torch.zeros(5, dtype=torch.int64, device="cuda")
+    st = torch.zeros(5, dtype=torch.int32, device="cuda")
+    ss.hackrf_prepass_device(d.data_ptr(), 5, 65536, f.data_ptr(), st.data_ptr())
+    torch.cuda.synchronize()
+    print("hackrf prepass", f.cpu().tolist(), st.cpu().tolist(), flush=True)
