@@ -175,15 +175,15 @@ def cpu_baseline(wl: dict, window: np.ndarray, threshold: float, use_w: int, tar
     raw = synth_host(wl, n_buf, seed=991)
     threads = threads or O.hardware_threads()
     sec, _, _ = O.bench(raw, wl["n"], wl["fs"], wl["enob"], wl["kind"], wl["dc"], 1, threshold, window, use_w,
-                        repeats=1, threads=threads, faithful=True)
+                        repeats=1, threads=threads, faithful=2)
     repeats = max(1, int(target_s / max(sec, 1e-6)))
     sec, hits, threads = O.bench(raw, wl["n"], wl["fs"], wl["enob"], wl["kind"], wl["dc"], 1, threshold, window,
-                                 use_w, repeats=repeats, threads=threads, faithful=True)
+                                 use_w, repeats=repeats, threads=threads, faithful=2)
     samples = n_buf * wl["n"] * repeats
     return {"value": samples / sec / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_buf} synthetic buffers of the workload x {repeats} repeats "
                       f"({samples / 1e6:.0f} Msamples, {sec:.1f} s), oracle restatement of "
-                      f"process.cpp:272-310 incl. the reference's per-buffer copies, one FFT plan per thread"}, sec
+                      f"process.cpp:272-310 incl. the reference's per-buffer copies; FFTs run 8 per AVX vector per thread (bit-identical to the scalar plan, tuned-library speed)"}, sec
 
 
 def cpu_fft_upper_bound(wl: dict, target_s: float = 3.0):
@@ -228,20 +228,20 @@ def run_reference(args) -> None:
     threads = O.hardware_threads()
     # size a step at ~1 s of CPU work
     sec, _, _ = O.bench(raw, wl["n"], wl["fs"], wl["enob"], wl["kind"], wl["dc"], 1, thr, window, use_w,
-                        repeats=1, threads=threads, faithful=True)
+                        repeats=1, threads=threads, faithful=2)
     repeats = max(1, int(1.0 / max(sec, 1e-6)))
     for _ in range(args.warmup):
         O.bench(raw, wl["n"], wl["fs"], wl["enob"], wl["kind"], wl["dc"], 1, thr, window, use_w,
-                repeats=repeats, threads=threads, faithful=True)
+                repeats=repeats, threads=threads, faithful=2)
     total = 0.0
     for _ in range(args.steps):
         s, _, _ = O.bench(raw, wl["n"], wl["fs"], wl["enob"], wl["kind"], wl["dc"], 1, thr, window, use_w,
-                          repeats=repeats, threads=threads, faithful=True)
+                          repeats=repeats, threads=threads, faithful=2)
         total += s
     samples_per_step = n_buf * wl["n"] * repeats
     value = samples_per_step * args.steps / total / 1e6
     sample = (f"each step = {n_buf} synthetic buffers x {repeats} repeats ({samples_per_step / 1e6:.0f} Msamples) "
-              f"through the oracle restatement of process.cpp:272-310 (reference copies kept), {threads} threads")
+              f"through the oracle restatement of process.cpp:272-310 (reference copies kept; FFTs 8 per AVX vector, bit-identical to the scalar plan), {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,

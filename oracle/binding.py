@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
         h.orc_fft_f32.restype = None
         h.orc_fft_f32.argtypes = [_VP, _VP, _U32]
         h.orc_fft_f64.restype = None
+        h.orc_fft_f32_batch8.argtypes = [_VP, _VP, _U32]
+        h.orc_fft_f32_batch8.restype = None
         h.orc_fft_f64.argtypes = [_VP, _VP, _U32]
         h.orc_magnitude_db.restype = None
         h.orc_magnitude_db.argtypes = [_VP, _VP, _U32, _I]
@@ -98,6 +100,15 @@ def fft_f32(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, np.complex64)
     out = np.empty_like(x)
     lib().orc_fft_f32(_p(x), _p(out), x.shape[0])
+    return out
+
+
+def fft_f32_batch8(x: np.ndarray) -> np.ndarray:
+    """x: [8][n][2] float32 -> eight forward FFTs through the SIMD-batched plan of the timed CPU baseline."""
+    x = np.ascontiguousarray(x, np.float32)
+    assert x.shape[0] == 8 and x.shape[2] == 2
+    out = np.empty_like(x)
+    lib().orc_fft_f32_batch8(_p(x), _p(out), x.shape[1])
     return out
 
 
@@ -170,8 +181,9 @@ def time_domain(raw: np.ndarray, n: int, enob: int, kind: int, correct_dc: bool,
 
 def bench(raw: np.ndarray, n: int, sample_rate: int, enob: int, kind: int, correct_dc: bool, averaging: int,
           threshold: float, window: np.ndarray, use_window_bins: int, dc_ignore_window: int = 4,
-          repeats: int = 1, threads: int = 0, faithful: bool = True):
-    """Returns (seconds, total_hits, threads_used)."""
+          repeats: int = 1, threads: int = 0, faithful=True):
+    """Returns (seconds, total_hits, threads_used).  faithful: False = fused CPU path, True = the reference's
+    per-buffer copies kept, 2 = the same with the FFTs run eight at a time per worker (SIMD across buffers)."""
     raw = np.ascontiguousarray(raw)
     nb = raw.nbytes // (n * bytes_per_sample(kind))
     window = np.ascontiguousarray(window, np.float32)
@@ -180,7 +192,7 @@ def bench(raw: np.ndarray, n: int, sample_rate: int, enob: int, kind: int, corre
         threads = int(lib().orc_hardware_threads()) or 1
     sec = lib().orc_bench(n, sample_rate, enob, kind, 1 if correct_dc else 0, max(1, averaging), threshold,
                           use_window_bins, dc_ignore_window, _p(window), _p(raw), nb, repeats, threads,
-                          1 if faithful else 0, C.byref(hits))
+                          int(faithful), C.byref(hits))
     return float(sec), int(hits.value), threads
 
 

@@ -139,3 +139,25 @@ def test_k1_averaging_is_identity():
         iq = O.window_apply(O.convert(3, raw[b], n, 12, False), w)
         db = O.magnitude_db(O.fft_f32(iq[:, 0] + 1j * iq[:, 1]))
         np.testing.assert_array_equal(a["spectra_db"][b].view(np.uint32), db.view(np.uint32))
+
+
+def test_batched_fft_of_the_timed_baseline_is_bit_identical_to_the_scalar_plan():
+    """bench.py's CPU arm runs its FFTs eight at a time (one per SIMD lane); same roundings, so same bits."""
+    rng = np.random.default_rng(11)
+    for n in (256, 1024, 2048, 8192):
+        x = rng.standard_normal((8, n, 2)).astype(np.float32)
+        got = O.fft_f32_batch8(x)
+        for l in range(8):
+            want = O.fft_f32(x[l].view(np.complex64).reshape(n)).view(np.float32).reshape(n, 2)
+            assert np.array_equal(got[l].view(np.uint32), want.view(np.uint32))
+
+
+def test_batched_baseline_counts_the_same_hits():
+    from tests import synth
+    n = 2048
+    raw = synth.make_buffers(1, n, 37, 8, seed=77)          # 4 groups of 8 + 5 leftovers
+    w, use_w = O.window_build(5, n), O.use_window(0.75, n)
+    a = O.bench(raw, n, 20_000_000, 8, 1, True, 1, 8.0, w, use_w, repeats=1, threads=3, faithful=True)
+    b = O.bench(raw, n, 20_000_000, 8, 1, True, 1, 8.0, w, use_w, repeats=1, threads=3, faithful=2)
+    res = O.pipeline(raw, n, 20_000_000, 8, 1, True, 1, 8.0, w, use_w, precision=0)
+    assert a[1] == b[1] == int(res["hit_count"].sum()) > 0
