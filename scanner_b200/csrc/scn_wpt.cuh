@@ -164,7 +164,23 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
   };
   uint32_t raw[32];                                                  // row r: samples 2*lane, 2*lane+1 (+ 64 r)
   uint32_t s_cur = gw;
+  // EXPERIMENT, default off, not yet measured: ncu shows no_instruction stalls (0.43 warps per issue) -- the 41 KB
+  // loop body misses the L0 instruction cache while the two warps of a scheduler drift apart.  SCN_WPT_PAIRSYNC=1
+  // keeps the warps of a CTA on the same transform index with one CTA barrier per transform, so they fetch
+  // the same instructions.  Every warp of the CTA arrives the same number of times: iterations of warp 0.
+#ifndef SCN_WPT_PAIRSYNC
+#define SCN_WPT_PAIRSYNC 0
+#endif
+#if SCN_WPT_PAIRSYNC
+  const uint32_t gw0 = blockIdx.x * kWptWarpsPerCta;
+  uint32_t pair_iters = gw0 < p.n_spectra ? (p.n_spectra - gw0 + nw - 1) / nw : 0u;   // warp 0 runs the most
+  if (s_cur >= p.n_spectra) {
+    for (; pair_iters; pair_iters--) __syncthreads();
+    return;
+  }
+#else
   if (s_cur >= p.n_spectra) return;
+#endif
 #if SCN_WPT_TMA
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -181,6 +197,10 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
 #endif
 
   while (true) {
+#if SCN_WPT_PAIRSYNC
+    __syncthreads();
+    pair_iters--;
+#endif
 #if SCN_WPT_TMA
     mbar_wait(bar, phase);                        // this transform's bytes have landed
     phase ^= 1u;
@@ -335,6 +355,9 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     if (!has_next) break;
     s_cur = s_next;
   }
+#if SCN_WPT_PAIRSYNC
+  for (; pair_iters; pair_iters--) __syncthreads();   // a warp that ran one transform fewer still arrives
+#endif
 }
 
 }  // namespace scn
