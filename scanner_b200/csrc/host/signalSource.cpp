@@ -4,10 +4,10 @@
 
 SignalSource::SignalSource(uint32_t sampleRate, uint32_t sampleCount, double startFrequency,
                            double stopFrequency, double useBandWidth, double dcIgnoreWidth, bool doTiming)
-    : m_doTiming(doTiming), m_retuneTime(doTiming ? s_maxIndex : 0), m_getSamplesTime(doTiming ? s_maxIndex : 0),
-      m_sampleRate(sampleRate), m_sampleCount(sampleCount), m_startFrequency(startFrequency),
+    : m_sampleRate(sampleRate), m_sampleCount(sampleCount), m_startFrequency(startFrequency),
       m_stopFrequency(stopFrequency),
-      m_frequencyTable(sampleRate, startFrequency, stopFrequency, useBandWidth, dcIgnoreWidth) {}
+      m_frequencyTable(sampleRate, startFrequency, stopFrequency, useBandWidth, dcIgnoreWidth),
+      m_doTiming(doTiming), m_retuneTime(doTiming ? s_maxIndex : 0), m_getSamplesTime(doTiming ? s_maxIndex : 0) {}
 
 SignalSource::~SignalSource() {
   if (m_thread && m_thread->joinable()) {
