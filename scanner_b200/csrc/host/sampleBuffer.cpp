@@ -1,7 +1,11 @@
 #include "sampleBuffer.h"
 
 #include <cassert>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+
+#include "scanner_b200.h"
 
 SampleBuffer::SampleBuffer(SampleKind kind, uint32_t enob, uint32_t count, uint32_t capacityBuffers)
     : m_kind(kind), m_sampleCount(count), m_enob(enob), m_capacity(capacityBuffers ? capacityBuffers : 1),
@@ -70,6 +74,30 @@ uint32_t SampleBuffer::GetNextSamples(ProcessInterface<uint8_t>* process, std::v
   }
   process->End();
   return uint32_t(taken.size());
+}
+
+bool SampleBuffer::GetNextSamples(fftwf_complex* outputBuffer, double& centerFrequency) {
+  Item item;
+  {
+    std::unique_lock<std::mutex> lock(m_mutex);
+    m_conditionEmpty.wait(lock, [this] { return m_done || !m_queue.empty(); });
+    if (m_queue.empty()) return false;
+    const bool wake = m_queue.size() >= m_capacity;
+    item = std::move(m_queue.front());
+    m_queue.pop_front();
+    if (wake) m_conditionFull.notify_all();
+  }
+  centerFrequency = item.frequency;
+  if (m_kind == FloatComplex) {
+    memcpy(outputBuffer, item.raw.data(), m_bufferBytes);
+  } else {
+    if (!m_convert) { fprintf(stderr, "SampleBuffer: int16 samples need a converter (SetConverter)\n"); exit(1); }
+    if (!m_convert(item.raw.data(), 1, &outputBuffer[0][0])) {
+      fprintf(stderr, "SampleBuffer: sample conversion failed: %s\n", scn_last_error());
+      exit(1);
+    }
+  }
+  return true;
 }
 
 void SampleBuffer::SetIsDone() {

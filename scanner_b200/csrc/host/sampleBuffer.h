@@ -26,6 +26,13 @@ class SampleBuffer {
   // empty.  centerFrequencies receives one entry per visited buffer.
   uint32_t GetNextSamples(ProcessInterface<uint8_t>* process, std::vector<double>& centerFrequencies,
                           uint32_t maxBuffers = 1);
+  // The reference's own drain (sampleBuffer.h:44, sampleBuffer.cpp:127-152): the next buffer as fftwf_complex.
+  // fc32 buffers are copied; int16 kinds go through the converter installed with SetConverter (scn_convert_host
+  // of a context of this kind: the reference's converter arithmetic on the GPU) -- without one the call fails
+  // loudly, there is no CPU converter in this library.  false == done and empty.
+  typedef SampleQueue::Converter Converter;
+  void SetConverter(Converter convert) { m_convert = convert; }
+  bool GetNextSamples(fftwf_complex* outputBuffer, double& centerFrequency);
   void SetIsDone();
   bool GetIsDone();
   // SCN_KIND_* of this buffer's samples, for scn_config.sample_kind
@@ -42,4 +49,5 @@ class SampleBuffer {
   std::mutex m_mutex;
   std::condition_variable m_conditionEmpty, m_conditionFull;
   bool m_done = false;
+  Converter m_convert;
 };

@@ -202,6 +202,24 @@ int main(int argc, char** argv) {
     CHECK(sb.GetNextSamples(&v, f, 3) == 2 && v.seq == 3 * N && f[0] == 103.0);
     CHECK(sb.GetNextSamples(&v, f, 3) == 0);
   }
+  // ---- SampleBuffer: the reference's own drain signature (sampleBuffer.h:44) on fc32 buffers
+  {
+    const uint32_t N = 64;
+    SampleBuffer sb(SampleBuffer::FloatComplex, 0, N, 4);
+    std::vector<float> in(2 * N), out(2 * N);
+    for (int b = 0; b < 3; b++) {
+      for (uint32_t i = 0; i < 2 * N; i++) in[i] = float(b * 100 + int(i));
+      sb.AppendSamples(reinterpret_cast<fftwf_complex*>(in.data()), 1e6 * (b + 1));
+    }
+    sb.SetIsDone();
+    double f = 0;
+    for (int b = 0; b < 3; b++) {
+      CHECK(sb.GetNextSamples(reinterpret_cast<fftwf_complex*>(out.data()), f));
+      CHECK(f == 1e6 * (b + 1) && out[9] == float(b * 100 + 9));
+    }
+    CHECK(!sb.GetNextSamples(reinterpret_cast<fftwf_complex*>(out.data()), f));
+  }
+
   // ---- triggered recording (messageQueue.h:98-139, 259-288) on fc32 messages (no conversion, no GPU)
   {
     const uint32_t N = 256;
