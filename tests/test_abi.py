@@ -84,3 +84,23 @@ def test_shard_steps_partitions():
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
     assert [S.shard_steps(133, r, 8) for r in range(8)][0] == (0, 16)
+
+
+def test_frequency_table_random_sweeps_agree_with_oracle_and_reference_tool():
+    """frequencyTable.cpp:9-37 over random sweeps: C ABI helper == oracle, and == the reference's own code when
+    oracle/_ref is present (the build container)."""
+    from oracle import ref as R
+    rng = np.random.default_rng(7)
+    for k in range(60):
+        fs = int(rng.choice([2_400_000, 8_000_000, 10_000_000, 20_000_000, 56_000_000]))
+        start = float(rng.integers(50, 5000)) * 1e6
+        span = float(rng.integers(1, 1200)) * 1e6
+        stop = 0.0 if k % 10 == 0 else start + span
+        use_bw = float(rng.choice([0.75, 0.5, 0.9]))
+        dc_ignore = float(rng.choice([0.0, 0.0, 0.05]))
+        a = S.frequency_table(fs, start, stop, use_bw, dc_ignore)
+        b = O.frequency_table(fs, start, stop, use_bw, dc_ignore)
+        np.testing.assert_array_equal(a, b)
+        assert len(a) >= 1
+        if R.available() and k < 12:
+            np.testing.assert_array_equal(a, R.frequency_table(fs, start, stop, use_bw, dc_ignore))
