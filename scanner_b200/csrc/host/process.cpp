@@ -30,9 +30,7 @@ ProcessSamples::ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_
   if (scn_window_build(windowType, numSamples, m_window.data()) != SCN_OK) Die("FFTWindow");
 }
 
-ProcessSamples::~ProcessSamples() {
-  if (m_writeCtx) scn_destroy(m_writeCtx);
-}
+ProcessSamples::~ProcessSamples() {}
 
 // Hit records per spectrum copied back with every batch; a spectrum with more hits than this is re-run
 // alone through a full-capacity context (rare: the reference itself treats > 1047 hits as an event,
@@ -237,10 +235,11 @@ bool ProcessSamples::StartProcessing(SampleQueue& sampleQueue) {
   if (!m_fileNameBase.empty() && sampleQueue.m_kind != SampleQueue::FloatComplex && !m_writeCtx) {
     // recording writes fftwf_complex (messageQueue.h:127-130); the queue holds raw samples, so its writer thread
     // converts each recorded message with the reference's converter arithmetic on the GPU
-    m_writeCtx = CreateContext(sampleQueue.m_kind, sampleQueue.GetEnob(), sampleQueue.GetCorrectDCOffset(), 1, 1);
-    scn_ctx* ctx = m_writeCtx;
+    m_writeCtx.reset(CreateContext(sampleQueue.m_kind, sampleQueue.GetEnob(), sampleQueue.GetCorrectDCOffset(), 1, 1),
+                     [](scn_ctx* c) { scn_destroy(c); });
+    std::shared_ptr<scn_ctx> ctx = m_writeCtx;
     sampleQueue.SetWriteConverter([ctx](const void* raw, uint32_t nBuffers, float* out) {
-      return scn_convert_host(ctx, raw, nBuffers, out) == SCN_OK;
+      return scn_convert_host(ctx.get(), raw, nBuffers, out) == SCN_OK;
     });
   }
   for (uint32_t t = 0; t < m_threadCount; t++) {

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -83,7 +84,8 @@ class ProcessSamples {
   std::atomic<bool> m_writing{false};
   std::atomic<uint64_t> m_endSequenceId{0};
   uint32_t m_fileCounter = 0;                      // process.cpp:169
-  scn_ctx* m_writeCtx = nullptr;                   // converts recorded messages (scn_convert_host), writer thread only
+  std::shared_ptr<scn_ctx> m_writeCtx;             // converts recorded messages (scn_convert_host), writer thread only;
+                                                   // shared with the queue's converter so either may be destroyed first
   std::function<time_t()> m_clock;                 // file-name stamps; default time(NULL)
  public:
   void SetClock(std::function<time_t()> clock) { m_clock = std::move(clock); }   // reproducible replays
