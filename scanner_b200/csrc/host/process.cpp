@@ -180,7 +180,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
         lastFrequency = header.m_frequency;
       }
     }
-    for (auto* m : f.batch) q->MessageProcessed(m);       // process.cpp:309
+    q->MessageProcessed(f.batch);                         // process.cpp:309, one lock for the batch
     m_buffersProcessed += f.batch.size();
     f.batch.clear();
     f.active = false;

@@ -63,10 +63,17 @@ SampleQueue::~SampleQueue() {
 }
 
 SampleQueue::MessageType* SampleQueue::Allocate() {
-  std::unique_lock<std::mutex> lock(m_poolMutex);
-  m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
-  MessageType* m = m_free.back();
-  m_free.pop_back();
+  std::unique_lock<std::mutex> cacheLock(m_allocMutex);          // uncontended with a single producer
+  if (m_allocCache.empty()) {
+    std::unique_lock<std::mutex> lock(m_poolMutex);
+    m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
+    for (size_t i = 0; i < kAllocChunk && !m_free.empty(); i++) {
+      m_allocCache.push_back(m_free.back());
+      m_free.pop_back();
+    }
+  }
+  MessageType* m = m_allocCache.back();
+  m_allocCache.pop_back();
   return m;
 }
 
@@ -95,9 +102,11 @@ void SampleQueue::SynchronizedAppend(const void* a, size_t aBytes, const void* b
   std::unique_lock<std::mutex> lock(m_mutex);
   header.m_sequenceId = m_nextBufferSequenceId++;
   m_conditionFull.wait(lock, [this] { return m_buffer.size() < m_bufferCount; });
-  const bool wake = m_buffer.empty();
   m_buffer.push_back(message);
-  if (wake) m_conditionEmpty.notify_all();
+  // wake consumers once what the least demanding waiter asked for is queued.  (Waking only on the empty ->
+  // non-empty edge, as the reference's single-message consumers do, would strand a consumer that waits for a
+  // group of K > 1 buffers: it wakes at 1, goes back to sleep, and nobody notifies again.)
+  if (m_waiters && m_buffer.size() >= m_waitNeed) m_conditionEmpty.notify_all();
   ClearAck();
 }
 
@@ -122,9 +131,17 @@ void SampleQueue::AppendSamples(fftwf_complex* floatComplexSamples, double cente
   SynchronizedAppend(floatComplexSamples, m_bufferBytes, nullptr, 0, centerFrequency, time);
 }
 
+void SampleQueue::WaitForQueued(std::unique_lock<std::mutex>& lock, uint32_t need) {
+  if (m_done || m_buffer.size() >= need) return;
+  m_waiters++;
+  if (m_waitNeed == 0 || need < m_waitNeed) m_waitNeed = need;
+  m_conditionEmpty.wait(lock, [&] { return m_done || m_buffer.size() >= need; });
+  if (--m_waiters == 0) m_waitNeed = 0;
+}
+
 SampleQueue::MessageType* SampleQueue::GetNextSamples() {
   std::unique_lock<std::mutex> lock(m_mutex);
-  m_conditionEmpty.wait(lock, [this] { return m_done || !m_buffer.empty(); });
+  WaitForQueued(lock, 1);
   if (m_buffer.empty()) return nullptr;
   const bool wake = m_buffer.size() >= m_bufferCount;
   MessageType* message = m_buffer.front();
@@ -139,7 +156,7 @@ uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxC
   if (multiple == 0) multiple = 1;
   std::unique_lock<std::mutex> lock(m_mutex);
   // a group of `multiple` buffers forms one averaged spectrum: wait for a whole group (or the end)
-  if (wait) m_conditionEmpty.wait(lock, [&] { return m_done || m_buffer.size() >= multiple; });
+  if (wait) WaitForQueued(lock, multiple);
   else if (!(m_done || m_buffer.size() >= multiple)) return 0;
   size_t take = m_buffer.size() < maxCount ? m_buffer.size() : maxCount;
   if (!(m_done && m_buffer.size() <= maxCount)) take -= take % multiple;
@@ -176,6 +193,24 @@ void SampleQueue::TrimWriteHistory() {
     Free(oldest->second);
     m_writeBuffer.erase(oldest);
   }
+}
+
+void SampleQueue::MessageProcessed(const std::vector<MessageType*>& messages) {
+  if (messages.empty()) return;
+  if (!m_doWrite) {
+    std::unique_lock<std::mutex> lock(m_poolMutex);
+    for (MessageType* m : messages) {
+      assert(m->m_header.m_kind != MessageHeader::Illegal);
+      m->m_header.m_kind = MessageHeader::Free;
+      m_free.push_back(m);
+    }
+    m_poolAvailable.notify_all();
+    return;
+  }
+  std::unique_lock<std::mutex> lock(m_writeMutex);
+  for (MessageType* m : messages) m_writeBuffer[m->m_header.m_sequenceId] = m;
+  TrimWriteHistory();
+  m_conditionWrite.notify_all();
 }
 
 void SampleQueue::SetWriteConverter(Converter convert) {

@@ -81,6 +81,9 @@ class SampleQueue {
   uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1,
                         bool wait = true);
   void MessageProcessed(MessageType* message);
+  // the same for a whole drained batch under ONE pool / history lock (a consumer that returns 1024 messages one by
+  // one fights the producer's Allocate for the pool mutex 1024 times)
+  void MessageProcessed(const std::vector<MessageType*>& messages);
 
   void BeginWrite(uint64_t startSequenceId, std::string fileName);
   void EndWrite(uint64_t sequenceId);
@@ -107,6 +110,8 @@ class SampleQueue {
                           double centerFrequency, time_t time);
   MessageType* Allocate();
   void Free(MessageType* m);
+  void WaitForQueued(std::unique_lock<std::mutex>& lock, uint32_t need);   // m_mutex held
+  uint32_t m_waiters = 0, m_waitNeed = 0;      // consumers asleep on m_conditionEmpty / the smallest count one waits for
 
   uint32_t m_enob;
   uint32_t m_sampleCount;
@@ -146,5 +151,10 @@ class SampleQueue {
   std::condition_variable m_poolAvailable;
   std::vector<MessageType> m_messages;
   std::vector<MessageType*> m_free;
+  // free messages the appending side has already taken out of the pool (refilled kAllocChunk at a time, so the
+  // producer touches the contended pool mutex once per chunk instead of once per buffer)
+  static const size_t kAllocChunk = 32;
+  std::mutex m_allocMutex;
+  std::vector<MessageType*> m_allocCache;
   void* m_slab = nullptr;                     // one pinned allocation backing every message
 };

@@ -44,8 +44,57 @@ static std::vector<char> ReadAll(const char* path) {
 // host_selftest hackrf_queue <N> <fs> <start> <stop> <iterations> <valid_length> <stream_file> <out_file>
 //   replays the capture through RxCallback into a SampleQueue (no GPU) and dumps, per accepted message,
 //   { double frequency, int64 time, uint64 sequenceId, raw bytes }.
+// host_selftest queuebench <kind> <N> <total_buffers> [consumers] [max_batch] [busy_us_per_batch]
+//   throughput of the hand-off alone (no GPU): one producer appends `total` buffers, consumers drain batches and
+//   return the messages at once.  Tells how much of the plugin-surface time is the queue itself.
+static int QueueBench(int argc, char** argv) {
+  const int kind = atoi(argv[2]);
+  const uint32_t n = atoi(argv[3]);
+  const size_t total = strtoull(argv[4], nullptr, 0);
+  const uint32_t consumers = argc > 5 ? atoi(argv[5]) : 1;
+  const uint32_t maxBatch = argc > 6 ? atoi(argv[6]) : 1024;
+  const uint32_t busyUs = argc > 7 ? atoi(argv[7]) : 0;       // stand-in for the launch + collect time of a batch
+  SampleQueue q(SampleQueue::SampleKind(kind), 8, n, 1024, false, false);
+  q.SetDropFirstSweep(false);
+  const size_t bb = q.GetBufferBytes();
+  std::vector<char> raw(bb * 64, 1);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::thread producer([&] {
+    for (size_t b = 0; b < total; b++) {
+      char* p = raw.data() + (b % 64) * bb;
+      if (kind == SampleQueue::ByteComplex) q.AppendSamples(reinterpret_cast<int8_t(*)[2]>(p), 1e6, 0);
+      else if (kind == SampleQueue::ShortComplex) q.AppendSamples(reinterpret_cast<int16_t(*)[2]>(p), 1e6, 0);
+      else q.AppendSamples(reinterpret_cast<fftwf_complex*>(p), 1e6, 0);
+    }
+    q.SetIsDone();
+  });
+  std::atomic<uint64_t> seen{0};
+  std::vector<std::thread> pool;
+  for (uint32_t c = 0; c < consumers; c++)
+    pool.emplace_back([&] {
+      std::vector<SampleQueue::MessageType*> batch;
+      std::vector<char> staging(bb * maxBatch);
+      while (uint32_t got = q.GetNextBatch(batch, maxBatch, 1, true)) {
+        for (uint32_t i = 0; i < got; i++) memcpy(staging.data() + size_t(i) * bb, batch[i]->GetData(), bb);   // the consumer's copy
+        if (busyUs) {
+          const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(busyUs);
+          while (std::chrono::steady_clock::now() < until) {}
+        }
+        q.MessageProcessed(batch);
+        seen += got;
+      }
+    });
+  producer.join();
+  for (auto& t : pool) t.join();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("queuebench kind %d N %u: %lu buffers in %.3f s = %.1f Msamples/s = %.2f GB/s (%u consumer(s), batch <= %u)\n", kind, n,
+         (unsigned long)seen.load(), sec, double(seen) * n / sec / 1e6, double(seen) * bb / sec / 1e9, consumers, maxBatch);
+  return 0;
+}
+
 static int HackrfModes(int argc, char** argv) {
   const std::string cmd = argv[1];
+  if (cmd == "queuebench" && argc >= 5) return QueueBench(argc, argv);
   const uint32_t n = atoi(argv[2]), fs = uint32_t(atof(argv[3]));
   const double start = atof(argv[4]), stop = atof(argv[5]);
   if (cmd == "hackrf_prepass" && argc == 9) {
@@ -168,6 +217,29 @@ int main(int argc, char** argv) {
     producer.join();
     CHECK(total == 10);
     CHECK(!q.ReceivedAck()); q.SendAck(); CHECK(q.ReceivedAck()); q.ClearAck(); CHECK(!q.ReceivedAck());
+  }
+
+  {
+    // a consumer asleep waiting for a GROUP of buffers (K-FFT averaging) is woken when the group completes, not
+    // only on the empty -> non-empty edge (regression: it used to sleep forever once it had seen 1 < K buffers)
+    const uint32_t N = 16;
+    SampleQueue q(SampleQueue::ByteComplex, 8, N, 64, true, false);
+    q.SetDropFirstSweep(false);
+    std::thread producer([&] {
+      std::vector<int8_t> buf(2 * N, 1);
+      for (int b = 0; b < 8; b++) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(15));     // the consumer is asleep again by now
+        q.AppendSamples(reinterpret_cast<int8_t(*)[2]>(buf.data()), b, 0);
+      }
+    });
+    std::vector<SampleQueue::MessageType*> batch;
+    CHECK(q.GetNextBatch(batch, 4, 4) == 4);
+    q.MessageProcessed(batch);
+    CHECK(q.GetNextBatch(batch, 8, 4) == 4);
+    q.MessageProcessed(batch);
+    producer.join();
+    q.SetIsDone();
+    CHECK(q.GetNextBatch(batch, 8, 4) == 0);
   }
 
   // ---- SyntheticSource: deterministic, kind layouts, drives a queue through sweeps
