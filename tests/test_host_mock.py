@@ -1,0 +1,160 @@
+"""The HOST layer (SampleQueue, ProcessSamples, sources, scan_b200's wiring) against the reference's golden stdout
+and recording files WITHOUT a GPU: the same C++ sources are linked against tests/mock_abi (the C ABI implemented with
+the oracle -- test infrastructure, never shipped) instead of libscanner_b200.so.  What the GPU tests in
+test_host_surface.py / test_hackrf_sweep.py / test_record.py check through the real library, these check for the
+host logic alone -- including under ThreadSanitizer."""
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as O                      # noqa: E402,F401  (builds oracle/_build/liboracle.so)
+from tests import golden_util as GU     # noqa: E402
+
+G = GU.load()
+GH = np.load(os.path.join(ROOT, "tests", "golden", "hackrf_vectors.npz"), allow_pickle=False)
+GR = np.load(os.path.join(ROOT, "tests", "golden", "record_vectors.npz"), allow_pickle=False)
+ENV = dict(os.environ, TZ="UTC")
+HOST = os.path.join(ROOT, "scanner_b200", "csrc", "host")
+SRCS = [os.path.join(ROOT, "scanner_b200", "csrc", "tools", "scan_b200.cpp"),
+        os.path.join(ROOT, "tests", "mock_abi", "mock_scanner_abi.cpp")] + \
+       sorted(os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp"))
+
+
+def build(path, extra):
+    lib = os.path.join(ROOT, "oracle", "_build")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, *extra, "-o", path, *SRCS,
+           "-L" + lib, "-loracle", "-lpthread", "-Wl,-rpath," + lib]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return path
+
+
+@pytest.fixture(scope="module")
+def tool(tmp_path_factory):
+    return build(str(tmp_path_factory.mktemp("mock") / "scan_mock"), [])
+
+
+def replay(tool, case, tmp_path, threads=1, legacy=False, prefix=()):
+    rp, fp = str(tmp_path / "raw.bin"), str(tmp_path / "freq.bin")
+    np.ascontiguousarray(case["raw"]).tofile(rp)
+    np.ascontiguousarray(case["freqs"], np.float64).tofile(fp)
+    cmd = [*prefix, tool, "replay", str(case["kind"]), str(case["n"]), repr(float(case["fs"])), str(case["enob"]),
+           "1" if case["dc"] else "0", repr(case["thr"]), str(case["win"]), str(case["mode"]), str(case["per_sweep"]), rp, fp,
+           str(threads)] + (["legacy"] if legacy else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=ENV)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r
+
+
+@pytest.mark.parametrize("case", [c for c in GU.scan_cases(G) if c["n"] >= 256], ids=lambda c: c["name"])
+def test_host_layer_prints_what_the_reference_prints(tool, case, tmp_path):
+    text, want = replay(tool, case, tmp_path).stdout, case["text"]
+    if case["mode"] == 2:
+        got_hits, want_hits = GU.parse_hits(text), GU.parse_hits(want)
+        assert [f for f, _ in got_hits] == [f for f, _ in want_hits] and want_hits
+        assert max(abs(a - b) for (_, a), (_, b) in zip(got_hits, want_hits)) < 1e-3 + 1e-6
+    else:
+        got_td, want_td = GU.parse_time_domain(text), GU.parse_time_domain(want)
+        assert [(s, f) for s, _, f, _ in got_td] == [(s, f) for s, _, f, _ in want_td] and want_td
+    strip = lambda t: [re.sub(r"power_db .*|Max signal .*|Start scan at .*", "", l) for l in t.splitlines()
+                       if not re.match(r"Frequency \d+:|Starting source thread|Stopping source thread", l)]
+    assert strip(text) == strip(want)
+
+
+def test_two_workers_report_every_hit(tool, tmp_path):
+    case = next(c for c in GU.scan_cases(G) if c["name"] == "i8_dc_2048")
+    got = sorted(GU.parse_hits(replay(tool, case, tmp_path, threads=2).stdout))
+    want = sorted(GU.parse_hits(case["text"]))
+    assert [f for f, _ in got] == [f for f, _ in want]
+
+
+def test_more_than_64_hits_falls_back_to_the_full_list(tool, tmp_path):
+    from tests import synth
+    case = dict(next(c for c in GU.scan_cases(G) if c["name"] == "i8_1024"))
+    n = case["n"]
+    window, use_w = O.window_build(case["win"], n), O.use_window(0.75, n)
+    res = O.pipeline(case["raw"], n, case["fs"], case["enob"], case["kind"], case["dc"], 1, 0.0, window, use_w, precision=0)
+    case["thr"] = float(np.float32(np.median(res["spectra_db"][:, synth.candidate_bins(n, use_w)])))
+    res = O.pipeline(case["raw"], n, case["fs"], case["enob"], case["kind"], case["dc"], 1, case["thr"], window, use_w, precision=0)
+    lo, hi = GU.accepted_range(case)
+    assert res["hit_count"][lo:hi].min() > 64
+    want = []
+    for b in range(lo, hi):
+        _, _, bins = O.detect(res["spectra_db"][b], use_w, 4, case["thr"])
+        want += [O.hit_frequency(case["freqs"][b], case["fs"], n, int(i)) for i in bins]
+    assert [f for f, _ in GU.parse_hits(replay(tool, case, tmp_path).stdout)] == want
+
+
+def test_averaged_sweep_through_the_queue_terminates(tool):
+    """K = 4 groups through SampleQueue::GetNextBatch (the wake-up regression) with two workers."""
+    r = subprocess.run([tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "8", "3",
+                        "7", "2", "4"], capture_output=True, text=True, timeout=120, env=ENV)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"buffers (\d+) hits (\d+) launches (\d+)", r.stderr)
+    assert m and int(m.group(1)) == 2 * 3 * 8            # 2 accepted sweeps x 3 steps x 8 buffers
+
+
+def test_hackrf_sweep_replay(tool, tmp_path):
+    n, fs, start, stop, thr, iterations, valid = [GH["sweep_params"][i] for i in range(7)]
+    f = str(tmp_path / "stream.bin")
+    GH["sweep_stream"].tofile(f)
+    r = subprocess.run([tool, "hackrf", str(int(n)), str(int(fs)), repr(float(start)), repr(float(stop)), repr(float(thr)),
+                        str(int(iterations)), str(int(valid)), f, "1"], capture_output=True, text=True, timeout=120, env=ENV)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = str(GH["sweep_text"])
+    got_hits, want_hits = GU.parse_hits(r.stdout), GU.parse_hits(want)
+    assert [h for h, _ in got_hits] == [h for h, _ in want_hits] and want_hits
+    strip = lambda t: [re.sub(r"power_db .*", "", l) for l in t.splitlines()
+                       if not l.startswith("interpolateSamples") and not re.match(r"(Starting|Stopped) process thread", l)]
+    assert strip(r.stdout) == strip(want)
+
+
+def run_record(tool, tmp_path, prefix=()):
+    n, fs, enob, kind, dc, per_sweep, pre, post = [int(x) for x in GR["params"][:8]]
+    thr = float(GR["params"][8])
+    rp, fp = str(tmp_path / "raw.bin"), str(tmp_path / "freq.bin")
+    GR["raw"].tofile(rp)
+    GR["freqs"].astype(np.float64).tofile(fp)
+    r = subprocess.run([*prefix, tool, "record", str(kind), str(n), repr(float(fs)), str(enob), str(dc), repr(thr), "5",
+                        str(per_sweep), rp, fp, str(tmp_path / "rec-"), str(pre), str(post), "1"],
+                       capture_output=True, text=True, timeout=300, env=ENV)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r
+
+
+def test_recording_is_bit_identical_to_the_reference(tool, tmp_path):
+    r = run_record(tool, tmp_path)
+    got = r.stdout.replace(str(tmp_path) + os.sep, "")
+    pick = lambda t, pat: [l for l in str(t).splitlines() if re.match(pat, l)]
+    assert pick(got, r"BeginWrite|EndWrite") == pick(GR["text"], r"BeginWrite|EndWrite")
+    assert pick(got, r"Writing") == pick(GR["text"], r"Writing")
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("rec-"))
+    want = [(str(a), int(b), str(c)) for a, b, c in GR["files"]]
+    assert [f[len("rec-"):] for f in files] == [w[0] for w in want]
+    for f, (_, size, sha) in zip(files, want):
+        data = open(os.path.join(tmp_path, f), "rb").read()
+        assert len(data) == size and hashlib.sha256(data).hexdigest() == sha
+
+
+def test_host_layer_is_clean_under_thread_sanitizer(tmp_path):
+    """Two workers + the producer + (record mode) the writer thread, with ThreadSanitizer watching the host code."""
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")],
+                           input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime")
+    tsan = build(str(tmp_path / "scan_tsan"), ["-fsanitize=thread"])
+    prefix = ("setarch", "x86_64", "-R")                  # TSan wants a fixed address-space layout
+    env_ok = subprocess.run([*prefix, "true"], capture_output=True).returncode == 0
+    prefix = prefix if env_ok else ()
+    case = next(c for c in GU.scan_cases(G) if c["name"] == "i8_dc_2048")
+    r1 = replay(tsan, case, tmp_path, threads=2, prefix=prefix)
+    r2 = run_record(tsan, tmp_path, prefix=prefix)
+    for r in (r1, r2):
+        assert "ThreadSanitizer" not in r.stderr and "ThreadSanitizer" not in r.stdout, (r.stderr + r.stdout)[-4000:]
