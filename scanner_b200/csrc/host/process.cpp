@@ -106,6 +106,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   // more input: with nothing queued the in-flight batch is collected at once.
   struct InFlight {
     void* staging = nullptr;                       // contiguous pinned batch
+    const void* src = nullptr;                     // what was submitted: staging, or the batch's own slab run
     std::vector<SampleQueue::MessageType*> batch;
     uint32_t ticket = 0, nSpectra = 0;
     bool active = false;
@@ -116,6 +117,22 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * cap : 0);
   std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
 
+  const bool zeroCopy = m_zeroCopy && q->IsPinnedSlab();
+  // where the batch is submitted from: its own run of the pinned slab when it is one, else a copy in `staging`
+  auto stage = [&](InFlight& f) {
+    const uint32_t count = f.nSpectra * K;
+    bool oneRun = zeroCopy && count > 0;
+    for (uint32_t i = 1; oneRun && i < count; i++)
+      oneRun = static_cast<char*>(f.batch[i]->GetData()) == static_cast<char*>(f.batch[i - 1]->GetData()) + bufBytes;
+    if (oneRun) {
+      f.src = f.batch[0]->GetData();
+      m_zeroCopyBatches++;
+      return;
+    }
+    for (uint32_t i = 0; i < count; i++)
+      memcpy(static_cast<char*>(f.staging) + size_t(i) * bufBytes, f.batch[i]->GetData(), bufBytes);
+    f.src = f.staging;
+  };
   bool processedAny = false;
   uint64_t lastSequenceId = 0;
   double lastFrequency = 0.0;
@@ -155,7 +172,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
               fullHits.resize(N);
             }
             uint32_t c2 = 0;
-            if (scn_process_host(fullCtx, static_cast<char*>(f.staging) + size_t(s) * K * bufBytes, 1, nullptr, nullptr,
+            if (scn_process_host(fullCtx, static_cast<const char*>(f.src) + size_t(s) * K * bufBytes, 1, nullptr, nullptr,
                                  &c2, fullHits.data(), nullptr) != SCN_OK)
               Die("scn_process_host");
             list = fullHits.data();
@@ -190,13 +207,12 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   while (true) {
     InFlight& next = slot[cur];
     InFlight& prev = slot[cur ^ 1];
-    const uint32_t n = q->GetNextBatch(next.batch, maxSpectra * K, K, /*wait=*/!prev.active);
+    const uint32_t n = q->GetNextBatch(next.batch, maxSpectra * K, K, /*wait=*/!prev.active, zeroCopy);
     if (n) {
       next.nSpectra = n / K;                              // a trailing partial group at end of stream is dropped
-      for (uint32_t i = 0; i < next.nSpectra * K; i++)
-        memcpy(static_cast<char*>(next.staging) + size_t(i) * bufBytes, next.batch[i]->GetData(), bufBytes);
+      stage(next);
       if (next.nSpectra) {
-        if (scn_submit(ctx, next.staging, next.nSpectra, &next.ticket) != SCN_OK) Die("scn_submit");
+        if (scn_submit(ctx, next.src, next.nSpectra, &next.ticket) != SCN_OK) Die("scn_submit");
         m_launches++;
       }
       next.active = true;
@@ -205,14 +221,13 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
     if (n) cur ^= 1;
     else if (!slot[0].active && !slot[1].active) {
       // nothing in flight and the non-blocking poll found nothing: block, or stop when drained
-      const uint32_t m = q->GetNextBatch(slot[cur].batch, maxSpectra * K, K, /*wait=*/true);
+      const uint32_t m = q->GetNextBatch(slot[cur].batch, maxSpectra * K, K, /*wait=*/true, zeroCopy);
       if (m == 0) break;
       InFlight& f = slot[cur];
       f.nSpectra = m / K;
-      for (uint32_t i = 0; i < f.nSpectra * K; i++)
-        memcpy(static_cast<char*>(f.staging) + size_t(i) * bufBytes, f.batch[i]->GetData(), bufBytes);
+      stage(f);
       if (f.nSpectra) {
-        if (scn_submit(ctx, f.staging, f.nSpectra, &f.ticket) != SCN_OK) Die("scn_submit");
+        if (scn_submit(ctx, f.src, f.nSpectra, &f.ticket) != SCN_OK) Die("scn_submit");
         m_launches++;
       }
       f.active = true;
@@ -232,6 +247,7 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
 
 bool ProcessSamples::StartProcessing(SampleQueue& sampleQueue) {
   m_sampleQueue = &sampleQueue;
+  if (m_zeroCopy) sampleQueue.SetFifoPool(true);
   if (!m_fileNameBase.empty() && sampleQueue.m_kind != SampleQueue::FloatComplex && !m_writeCtx) {
     // recording writes fftwf_complex (messageQueue.h:127-130); the queue holds raw samples, so its writer thread
     // converts each recorded message with the reference's converter arithmetic on the GPU

@@ -49,6 +49,11 @@ class ProcessSamples {
   void SetDevice(int device) { m_device = device; }
   void SetAveraging(uint32_t k) { m_averaging = k ? k : 1; }
   void SetMaxBatch(uint32_t maxBatch) { m_maxBatch = maxBatch ? maxBatch : 1; }
+  // Hand batches to scn_submit straight from the queue's pinned slab (no staging copy) whenever a drained batch is
+  // one contiguous address run; the queue then recycles its messages FIFO so that this is the common case.
+  // Off by default (not yet measured on a GPU; verified against the goldens through tests/mock_abi).
+  void SetZeroCopy(bool on) { m_zeroCopy = on; }
+  uint64_t GetZeroCopyBatches() const { return m_zeroCopyBatches; }
   void SetOutput(FILE* out) { m_out = out; }                               // nullptr silences printing
   void SetDetectionSink(std::function<void(const Detection&)> sink) { m_sink = std::move(sink); }
   uint64_t GetBuffersProcessed() const { return m_buffersProcessed; }
@@ -83,6 +88,8 @@ class ProcessSamples {
   std::atomic<uint64_t> m_buffersProcessed{0}, m_hitCount{0}, m_launches{0};
   std::atomic<bool> m_writing{false};
   std::atomic<uint64_t> m_endSequenceId{0};
+  bool m_zeroCopy = false;
+  std::atomic<uint64_t> m_zeroCopyBatches{0};
   uint32_t m_fileCounter = 0;                      // process.cpp:169
   std::shared_ptr<scn_ctx> m_writeCtx;             // converts recorded messages (scn_convert_host), writer thread only;
                                                    // shared with the queue's converter so either may be destroyed first

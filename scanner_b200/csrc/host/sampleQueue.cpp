@@ -68,12 +68,17 @@ SampleQueue::MessageType* SampleQueue::Allocate() {
     std::unique_lock<std::mutex> lock(m_poolMutex);
     m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
     for (size_t i = 0; i < kAllocChunk && !m_free.empty(); i++) {
-      m_allocCache.push_back(m_free.back());
-      m_free.pop_back();
+      if (m_fifoPool) {                      // oldest first: ascending slab addresses
+        m_allocCache.push_back(m_free.front());
+        m_free.pop_front();
+      } else {                               // most recently freed first (cache-warm)
+        m_allocCache.push_front(m_free.back());
+        m_free.pop_back();
+      }
     }
   }
-  MessageType* m = m_allocCache.back();
-  m_allocCache.pop_back();
+  MessageType* m = m_allocCache.front();
+  m_allocCache.pop_front();
   return m;
 }
 
@@ -150,8 +155,14 @@ SampleQueue::MessageType* SampleQueue::GetNextSamples() {
   return message;
 }
 
+void SampleQueue::SetFifoPool(bool fifo) {
+  std::unique_lock<std::mutex> cacheLock(m_allocMutex);
+  std::unique_lock<std::mutex> lock(m_poolMutex);
+  m_fifoPool = fifo;
+}
+
 uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple,
-                                   bool wait) {
+                                   bool wait, bool contiguous) {
   out.clear();
   if (multiple == 0) multiple = 1;
   std::unique_lock<std::mutex> lock(m_mutex);
@@ -159,7 +170,14 @@ uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxC
   if (wait) WaitForQueued(lock, multiple);
   else if (!(m_done || m_buffer.size() >= multiple)) return 0;
   size_t take = m_buffer.size() < maxCount ? m_buffer.size() : maxCount;
-  if (!(m_done && m_buffer.size() <= maxCount)) take -= take % multiple;
+  if (contiguous) {
+    size_t run = take ? 1 : 0;
+    while (run < take && static_cast<char*>(m_buffer[run]->m_data) ==
+                             static_cast<char*>(m_buffer[run - 1]->m_data) + m_bufferBytes) run++;
+    // at least one whole group even across a break (the caller copies such a batch): never starve on fragmentation
+    if (run >= multiple || run == take) take = run; else take = take < multiple ? take : multiple;
+  }
+  if (!(m_done && m_buffer.size() <= maxCount && take == m_buffer.size())) take -= take % multiple;
   if (take == 0) return 0;
   const bool wake = m_buffer.size() >= m_bufferCount;
   for (size_t i = 0; i < take; i++) {

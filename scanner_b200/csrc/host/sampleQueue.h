@@ -78,8 +78,14 @@ class SampleQueue {
   // unless the queue is done.  Returns the number taken (0 == done and drained).
   // wait == false: never blocks -- returns 0 when no whole group is queued yet (used by the consumer to
   // finish an in-flight batch instead of sleeping on the queue).
+  // contiguous == true: the batch stops where the next message does not follow the previous one in memory, so the
+  // whole batch is ONE address run of the pinned slab and can be handed to scn_submit without a staging copy.
   uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1,
-                        bool wait = true);
+                        bool wait = true, bool contiguous = false);
+  // Recycle messages first-in first-out (ascending slab addresses) instead of last-in first-out, so consecutive
+  // appends land in consecutive slab slots.  Off by default; ProcessSamples::SetZeroCopy turns it on.
+  void SetFifoPool(bool fifo);
+  bool IsPinnedSlab() const { return m_slab != nullptr; }
   void MessageProcessed(MessageType* message);
   // the same for a whole drained batch under ONE pool / history lock (a consumer that returns 1024 messages one by
   // one fights the producer's Allocate for the pool mutex 1024 times)
@@ -150,11 +156,12 @@ class SampleQueue {
   std::mutex m_poolMutex;
   std::condition_variable m_poolAvailable;
   std::vector<MessageType> m_messages;
-  std::vector<MessageType*> m_free;
+  std::deque<MessageType*> m_free;
+  bool m_fifoPool = false;
   // free messages the appending side has already taken out of the pool (refilled kAllocChunk at a time, so the
   // producer touches the contended pool mutex once per chunk instead of once per buffer)
   static const size_t kAllocChunk = 32;
   std::mutex m_allocMutex;
-  std::vector<MessageType*> m_allocCache;
+  std::deque<MessageType*> m_allocCache;
   void* m_slab = nullptr;                     // one pinned allocation backing every message
 };

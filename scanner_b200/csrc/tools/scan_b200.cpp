@@ -103,6 +103,7 @@ int main(int argc, char** argv) {
     SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
     source.Start();
     source.StartStreaming(1, queue);
+    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
     process.StartProcessing(queue);
     source.Join();
     fflush(stdout);
@@ -131,7 +132,8 @@ int main(int argc, char** argv) {
       SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, true);
       source.Start();
       source.StartStreaming(1, queue);
-      process.StartProcessing(queue);
+      if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+    process.StartProcessing(queue);
       source.Join();
     }                                                           // ~SampleQueue flushes and joins the writer
     fflush(stdout);
@@ -151,6 +153,7 @@ int main(int argc, char** argv) {
     ProcessSamples process(n, fs, 8, thr, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
     SampleQueue queue(SampleQueue::ByteComplex, 8, n, 1024, true, false);
     source.StartStreaming(iterations, queue);
+    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
     process.StartProcessing(queue);
     source.Join();
     fflush(stdout);
@@ -173,12 +176,14 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     source.Start();
     source.StartStreaming(iterations, queue);
+    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
     process.StartProcessing(queue);
     source.Join();
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     printf("Elapsed time = %f ms\n", ms);                         // scan.cpp:43-47
-    fprintf(stderr, "buffers %lu hits %lu launches %lu\n", (unsigned long)process.GetBuffersProcessed(),
-            (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount());
+    fprintf(stderr, "buffers %lu hits %lu launches %lu zero-copy batches %lu\n", (unsigned long)process.GetBuffersProcessed(),
+            (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount(),
+            (unsigned long)process.GetZeroCopyBatches());
     return 0;
   }
   if (cmd == "bench" && argc >= 8) {
@@ -213,13 +218,14 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     source.Start();
     source.StartStreaming(1, queue);
+    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
     process.StartProcessing(queue);
     source.Join();
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("plugin-surface throughput: %.1f Msamples/s (%zu buffers of %u samples, kind %d, %u worker threads, "
-           "batch <= %u, %lu hits, %lu launches, %.3f s)\n",
+           "batch <= %u, %lu hits, %lu launches of which %lu zero-copy, %.3f s)\n",
            double(total) * n / sec / 1e6, total, n, kind, threads, maxBatch, (unsigned long)process.GetHitCount(),
-           (unsigned long)process.GetLaunchCount(), sec);
+           (unsigned long)process.GetLaunchCount(), (unsigned long)process.GetZeroCopyBatches(), sec);
     return 0;
   }
   fprintf(stderr, "scan_b200: bad arguments\n");

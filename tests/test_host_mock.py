@@ -41,14 +41,14 @@ def tool(tmp_path_factory):
     return build(str(tmp_path_factory.mktemp("mock") / "scan_mock"), [])
 
 
-def replay(tool, case, tmp_path, threads=1, legacy=False, prefix=()):
+def replay(tool, case, tmp_path, threads=1, legacy=False, prefix=(), env=None):
     rp, fp = str(tmp_path / "raw.bin"), str(tmp_path / "freq.bin")
     np.ascontiguousarray(case["raw"]).tofile(rp)
     np.ascontiguousarray(case["freqs"], np.float64).tofile(fp)
     cmd = [*prefix, tool, "replay", str(case["kind"]), str(case["n"]), repr(float(case["fs"])), str(case["enob"]),
            "1" if case["dc"] else "0", repr(case["thr"]), str(case["win"]), str(case["mode"]), str(case["per_sweep"]), rp, fp,
            str(threads)] + (["legacy"] if legacy else [])
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=ENV)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env or ENV)
     assert r.returncode == 0, r.stderr[-2000:]
     return r
 
@@ -99,6 +99,30 @@ def test_averaged_sweep_through_the_queue_terminates(tool):
     assert r.returncode == 0, r.stderr[-2000:]
     m = re.search(r"buffers (\d+) hits (\d+) launches (\d+)", r.stderr)
     assert m and int(m.group(1)) == 2 * 3 * 8            # 2 accepted sweeps x 3 steps x 8 buffers
+
+
+@pytest.mark.parametrize("threads", [1, 2])
+def test_zero_copy_batches_give_the_same_output(tool, tmp_path, threads):
+    """ProcessSamples::SetZeroCopy: batches submitted straight from the queue's slab (FIFO pool, contiguous runs)."""
+    zc = dict(ENV, SCN_ZERO_COPY="1")
+    for name in ("i8_dc_2048", "i16split_256", "f32_hann_1024", "i16_dc_512"):
+        case = next((c for c in GU.scan_cases(G) if c["name"] == name), None)
+        if case is None:
+            continue
+        a = sorted(GU.parse_hits(replay(tool, case, tmp_path, threads=threads, env=zc).stdout))
+        b = sorted(GU.parse_hits(case["text"]))
+        assert [f for f, _ in a] == [f for f, _ in b] and b
+    # a long averaged sweep wraps the slab several times: most batches are zero-copy, none is lost
+    r = subprocess.run([tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "600", "4",
+                        "7", str(threads), "4"], capture_output=True, text=True, timeout=300, env=zc)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"buffers (\d+) hits (\d+) launches (\d+) zero-copy batches (\d+)", r.stderr)
+    assert m and int(m.group(1)) == 3 * 3 * 600
+    assert int(m.group(4)) > 0
+    base = subprocess.run([tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "600", "4",
+                           "7", str(threads), "4"], capture_output=True, text=True, timeout=300, env=ENV)
+    m0 = re.search(r"buffers (\d+) hits (\d+) launches (\d+) zero-copy batches (\d+)", base.stderr)
+    assert m0 and m0.group(1) == m.group(1) and m0.group(2) == m.group(2) and int(m0.group(4)) == 0
 
 
 def test_hackrf_sweep_replay(tool, tmp_path):
