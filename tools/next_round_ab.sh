@@ -21,3 +21,12 @@ for rep in 1 2; do
 done
 # correctness of the lockstep experiment before believing its number
 SCN_LIB=scanner_b200/variants/lib_pairsync.so python -m pytest tests/test_gpu_parity.py -q -m gpu -k "cfg2 or (all_sizes and 11)" 2>&1 | tail -2
+# plugin surface: staging copy vs zero-copy batches from the queue's slab (ProcessSamples::SetZeroCopy)
+for w in 1 2; do
+  scanner_b200/scan_b200 bench 1 2048 8 1 4096 2000000 $w | tail -1
+  SCN_ZERO_COPY=1 scanner_b200/scan_b200 bench 1 2048 8 1 4096 2000000 $w | tail -1
+done
+scanner_b200/scan_b200 bench 4 8192 0 0 512 200000 2 | tail -1
+SCN_ZERO_COPY=1 scanner_b200/scan_b200 bench 4 8192 0 0 512 200000 2 | tail -1
+# and its correctness on the real library
+SCN_ZERO_COPY=1 python -m pytest tests/test_host_surface.py tests/test_record.py -q -m gpu 2>&1 | tail -2
