@@ -54,6 +54,17 @@ WORKLOADS = {
 }
 
 
+def workload_config(name: str, wl: dict, spectrum: bool, n_steps: int) -> dict:
+    """The `config` object: the same keys and values on BOTH arms (the driver compares them), nothing that depends
+    on the arm, the GPU count or a calibrated value -- those live under `run`."""
+    return {"workload": name + ": " + wl["desc"], "fft_size": wl["n"], "averaging": wl["K"],
+            "retune_steps": n_steps, "sample_kind": {1: "int8 IQ", 2: "int16 split", 3: "int16 IQ", 4: "fp32 IQ"}[wl["kind"]],
+            "enob": wl["enob"], "dc_correction": bool(wl["dc"]), "sample_rate": wl["fs"],
+            "window": {1: "hann", 5: "blackman-harris"}[wl["win"]], "spectrum_written": bool(spectrum),
+            "threshold_rule": "99.9th percentile of candidate-bin dB on a fixed-seed sample, guard-banded",
+            "l2_policy": "inputs larger than L2 (GPU arm: >= 0.8 GB of raw IQ per GPU per step)"}
+
+
 def bytes_per_sample(kind: int) -> int:
     return {1: 2, 2: 4, 3: 4, 4: 8}[kind]
 
@@ -114,6 +125,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz, self._halt = [], set(), None, threading.Event()
+        self.power = []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -137,6 +149,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -152,7 +168,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=1.0)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "sm_mhz_min": min(self.samples) if self.samples else None,
+                "power_w_median": float(np.median(self.power)) if self.power else None,
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def nvml_index(torch, local_rank: int) -> int:
@@ -246,7 +264,9 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"]},
+        "config": workload_config(args.workload, wl, not args.no_spectrum,
+                                  len(O.frequency_table(wl["fs"], wl["start"], wl["stop"]))),
+        "run": {"threshold_db": thr, "threads": threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -281,6 +301,74 @@ def calibrate_threshold(wl: dict, window: np.ndarray, use_w: int) -> float:
 
 
 # ---------------------------------------------------------------------------------------------
+def plugin_surface(wl: dict) -> dict:
+    """The reference-facing C++ surface end to end: a source thread -> SampleQueue::AppendSamples (raw bytes into the
+    pinned slab) -> ProcessSamples workers -> scn_submit/scn_collect, i.e. what replaces scan.cpp:211-238, driven by the
+    `scan_b200 bench` tool on this workload's buffer shape.  Host-bound by design (one memcpy per buffer on the
+    producer, like the reference's queue)."""
+    import re
+    import subprocess
+    tool = os.path.join(ROOT, "scanner_b200", "scan_b200")
+    if not os.path.exists(tool):
+        return {"unavailable": "scanner_b200/scan_b200 not built"}
+    n, kind = wl["n"], wl["kind"]
+    total = max(20000, int(3.0e9 // n))            # ~3 Gsamples through the queue
+    cmd = [tool, "bench", str(kind), str(n), str(wl["enob"]), "1" if wl["dc"] else "0", "4096", str(total), "2"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": str(e)}
+    m = re.search(r"plugin-surface throughput: ([0-9.]+) Msamples/s \((.*)\)", out.stdout)
+    if not m:
+        return {"unavailable": (out.stdout + out.stderr)[-300:]}
+    return {"value": float(m.group(1)), "unit": UNIT, "detail": m.group(2),
+            "path": "ReplaySource thread -> SampleQueue -> ProcessSamples (2 workers) -> C ABI; K=1 per-buffer detection"}
+
+
+def kernel_only(torch, S, kind: int, n: int, K: int, dc: bool, win: int, enob: int, device: int, peak: float,
+                target_bytes: int = 512 << 20, reps: int = 5) -> dict:
+    """Kernel-only throughput of one (kind, N, K) configuration on device-resident random IQ larger than L2:
+    3 warm-up launches, `reps` timed ones (CUDA events on the launch stream, median).  per_config rows."""
+    dev = torch.device("cuda", device)
+    bps = bytes_per_sample(kind)
+    nbuf = max(K, (target_bytes // (n * bps)) // K * K)
+    ns = nbuf // K
+    if kind == 4:
+        raw = (0.05 * torch.randn((nbuf, n, 2), device=dev)).contiguous()
+    else:
+        amp = 20 if kind == 1 else 300
+        raw = torch.randint(-amp, amp, (nbuf, n, 2), device=dev, dtype=torch.int8 if kind == 1 else torch.int16)
+    w = S.window_build(win, n)
+    ctx = S.SpectrumSense(n, 20_000_000, enob, 40.0, w, sample_kind=kind, correct_dc_offset=dc, averaging=K,
+                          max_spectra=16, max_hits_per_spectrum=16, device=device)
+    d_spec = torch.empty((ns, n), dtype=torch.float32, device=dev)
+    d_mask = torch.empty((ns, n // 32), dtype=torch.int32, device=dev)
+    d_cnt = torch.empty((ns,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+
+    def go():
+        ctx.launch_device(raw.data_ptr(), ns, d_spec.data_ptr(), d_mask.data_ptr(), d_cnt.data_ptr(), 0, 0, st.cuda_stream)
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); go(); e1.record(st); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    samples = nbuf * n
+    bpsamp = bps + 4.0 / K + (n / 8 + 4) / (K * n)
+    out = {"kind": {1: "int8 IQ", 3: "int16 IQ", 4: "fp32 IQ"}[kind], "fft_size": n, "averaging": K, "dc": dc,
+           "kernel": ctx.kernel_name, "kernel_ms": ms, "msamples_per_s": samples / ms / 1e3,
+           "bytes_per_sample": bpsamp, "hbm_gbs": samples * bpsamp / ms / 1e6,
+           "hbm_frac": samples * bpsamp / ms / 1e6 / peak, "input_bytes": int(raw.numel() * raw.element_size())}
+    ctx.close()
+    del raw, d_spec, d_mask, d_cnt
+    torch.cuda.empty_cache()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,7 +380,12 @@ def main() -> None:
     ap.add_argument("--no-spectrum", action="store_true", help="detections only (S=0 in SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_config / sustained / plugin_e2e (N=1 extras)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-step records travel -- NVLink peer-memory windows (scn_exchange_*) or "
+                         "an NCCL all-gather on a side stream")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--sustain-seconds", type=float, default=3.5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -329,7 +422,6 @@ def main() -> None:
     # ---- shard: global units (spectra) in step-major order, contiguous range per rank ------------
     spectra_per_step_per_gpu = max(1, wl["buffers_per_step"] // K)
     units_per_step = spectra_per_step_per_gpu * world          # dwell grows with N (weak scaling)
-    total_units = units_per_step * n_steps
     shard = S.plan_shard(n_steps, units_per_step, rank, world)
     first_unit, n_spectra = shard.first_unit, shard.n_units
     n_buffers = n_spectra * K
@@ -339,26 +431,33 @@ def main() -> None:
     raw_bytes = raw.numel() * raw.element_size()
     assert raw_bytes == n_buffers * n * bytes_per_sample(kind)
 
+    HIT_CAP = 16
     flags = (S.OUT_SPECTRUM if spectrum else 0) | S.OUT_HITS
     e2e_chunk = min(n_spectra, max(1, (64 << 20) // (n * bytes_per_sample(kind) * K)))
     ctx = S.SpectrumSense(n, wl["fs"], wl["enob"], thr, window, sample_kind=kind, correct_dc_offset=wl["dc"],
-                          averaging=K, max_spectra=e2e_chunk, max_hits_per_spectrum=16, flags=flags,
+                          averaging=K, max_spectra=e2e_chunk, max_hits_per_spectrum=HIT_CAP, flags=flags,
                           device=local_rank, ticket_slots=3)
     words, rec_words = ctx.words, ctx.record_words
     d_spec = torch.empty((n_spectra, n), dtype=torch.float32, device=dev) if spectrum else None
     d_mask = torch.empty((n_spectra, words), dtype=torch.int32, device=dev)
     d_count = torch.empty((n_spectra,), dtype=torch.int32, device=dev)
-    # per-step records are double-buffered: the exchange of step i (side stream, high priority) overlaps
-    # the fused kernel of step i+1 (main stream)
-    d_recs = [torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)]
-    d_gathers = [torch.empty((world, n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
-    d_merged = torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
-    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    d_merged = torch.zeros((n_steps, rec_words), dtype=torch.int32, device=dev)
+    # records exchange (N > 1).  "peer": publish(i) + merge(i-1) on the main stream, both tiny kernels, no rank ever
+    # waits for another (scn_exchange.cu).  "nccl": all-gather + merge on a high-priority side stream, double-buffered.
+    xch = None
+    d_rec = torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev)
+    if world > 1 and args.exchange == "peer":
+        xch = S.open_record_exchange(local_rank, rank, world, n_steps, rec_words)
+    d_recs = [d_rec, torch.empty_like(d_rec)]
+    d_gathers = [torch.empty((world, n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)] \
+        if (world > 1 and xch is None) else None
+    side = torch.cuda.Stream(device=dev, priority=-1) if d_gathers is not None else None
     rec_ready = [torch.cuda.Event() for _ in range(2)]
     rec_free = [torch.cuda.Event() for _ in range(2)]
     step_no = [0]
+    last_seq = [0]
 
     kernel_events = []
 
@@ -373,22 +472,34 @@ def main() -> None:
             kernel_events.append((e0, e1))
         par = step_no[0] & 1
         step_no[0] += 1
-        if world > 1 and step_no[0] > 2:
+        if xch is not None or world == 1:
+            ctx.summarize_steps(d_mask.data_ptr(), d_count.data_ptr(), n_spectra, first_unit, units_per_step,
+                                n_steps, d_rec.data_ptr(), sh)
+            if xch is not None:
+                seq = xch.publish(d_rec.data_ptr(), sh)
+                if seq > 1:
+                    xch.merge(seq - 1, d_merged.data_ptr(), sh)      # the previous batch: its rows landed long ago
+                last_seq[0] = seq
+            return
+        if step_no[0] > 2:
             stream.wait_event(rec_free[par])                         # the exchange two steps ago is done with it
         ctx.summarize_steps(d_mask.data_ptr(), d_count.data_ptr(), n_spectra, first_unit, units_per_step,
                             n_steps, d_recs[par].data_ptr(), sh)
-        if world > 1:
-            rec_ready[par].record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(rec_ready[par])
-                S.gather_step_records(d_recs[par], world, out=d_gathers[par])   # NCCL all-gather, ~13 KB per rank
-                ctx.merge_step_records(d_gathers[par].data_ptr(), world, n_steps, d_merged.data_ptr(),
-                                       side.cuda_stream)
-                rec_free[par].record(side)
+        rec_ready[par].record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(rec_ready[par])
+            S.gather_step_records(d_recs[par], world, out=d_gathers[par])   # NCCL all-gather, ~13 KB per rank
+            ctx.merge_step_records(d_gathers[par].data_ptr(), world, n_steps, d_merged.data_ptr(),
+                                   side.cuda_stream)
+            rec_free[par].record(side)
 
     def drain() -> None:
-        if side is not None:
-            stream.wait_stream(side)                                 # the last exchange belongs to the timed region
+        """The last batch's exchange belongs to the timed region."""
+        if xch is not None:
+            if last_seq[0]:
+                xch.merge(last_seq[0], d_merged.data_ptr(), sh)
+        elif side is not None:
+            stream.wait_stream(side)
 
     def barrier() -> None:
         if world > 1:
@@ -426,8 +537,7 @@ def main() -> None:
 
     # ---- device-resident timing (value) ----------------------------------------------------------
     # NVML is initialised BEFORE the barrier: anything rank 0 does between the barrier and its
-    # first launch shows up as rank skew inside the other ranks' timed region (they wait for it in
-    # the first all-gather).
+    # first launch shows up as rank skew inside the other ranks' timed region.
     sampler = ClockSampler(nvml_index(torch, local_rank)) if rank == 0 else None
     for _ in range(args.warmup):
         step(False)
@@ -445,9 +555,12 @@ def main() -> None:
     clocks = sampler.stop() if sampler else None
     elapsed_ms = t0.elapsed_time(t1)
     launches = ctx.launch_count - launches0
+    if xch is not None:
+        launches += 2 * args.steps          # publish + merge per batch (scn_exchange kernels are not counted by the ctx)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     starts = [a for a, _ in kernel_events] + [t1]
     step_ms = [round(starts[i].elapsed_time(starts[i + 1]), 4) for i in range(len(starts) - 1)]
+    kern_ms_rank = kern_ms
     if world > 1:
         tmax = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -455,6 +568,29 @@ def main() -> None:
     total_samples = samples_per_rank * world
     ms_per_step = elapsed_ms / args.steps
     value = total_samples / (ms_per_step * 1e-3) / 1e6
+
+    # ---- the exchanged records are RIGHT (untimed): merged == sum / OR over the ranks' partial records, and the
+    # merged hit total == the all-reduced sum of the per-spectrum counts ---------------------------------------------
+    records_check = None
+    if world > 1:
+        if xch is not None and xch.status() != 0:
+            raise SystemExit(f"bench.py: record exchange timed out waiting for a peer (sequence {xch.status()})")
+        local = d_recs[(step_no[0] - 1) & 1] if xch is None else d_rec
+        sums = local[:, :2].clone().to(torch.int64)
+        ors = local[:, 2:].clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ors, op=dist.ReduceOp.BOR)
+        hits_total = d_count.to(torch.int64).sum().reshape(1)
+        dist.all_reduce(hits_total, op=dist.ReduceOp.SUM)
+        ok_sum = bool(torch.equal(d_merged[:, :2].to(torch.int64), sums))
+        ok_or = bool(torch.equal(d_merged[:, 2:], ors))
+        ok_hits = int(d_merged[:, 0].to(torch.int64).sum()) == int(hits_total[0])
+        ok_units = int(d_merged[:, 1].to(torch.int64).sum()) == units_per_step * n_steps
+        records_check = {"merged_equals_sum_of_partials": ok_sum, "merged_masks_equal_or_of_partials": ok_or,
+                         "merged_hit_total_equals_allreduced_counts": ok_hits, "hit_total": int(hits_total[0]),
+                         "every_unit_accounted": ok_units, "exchange": args.exchange}
+        if not (ok_sum and ok_or and ok_hits and ok_units):
+            raise SystemExit(f"bench.py: merged step records are wrong on rank {rank}: {records_check}")
 
     # ---- roofline of the dominant (fused) kernel -------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -501,10 +637,33 @@ def main() -> None:
         n_chunks = (n_spectra + e2e_chunk - 1) // e2e_chunk
         h_counts = np.empty(n_spectra, np.uint32)
         h_masks = np.empty((n_spectra, words), np.uint32)
-        h_hits = np.zeros((n_spectra, 16), S.hit_dtype)
+        h_hits = np.zeros((n_spectra, HIT_CAP), S.hit_dtype)
+
+        # bare-copy ceiling: the same chunks, pinned host -> device, three streams, nothing else; every rank at once
+        cp_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        d_land = [torch.empty(chunk_bytes, dtype=torch.uint8, device=dev) for _ in range(3)]
+
+        def copy_pass() -> None:
+            for c in range(n_chunks):
+                nb = min(chunk_bytes, raw_bytes - c * chunk_bytes)
+                with torch.cuda.stream(cp_streams[c % 3]):
+                    d_land[c % 3][:nb].copy_(host_t[c * chunk_bytes: c * chunk_bytes + nb], non_blocking=True)
+            torch.cuda.synchronize()
+        copy_pass()
+        barrier()
+        c0 = time.perf_counter()
+        for _ in range(3):
+            copy_pass()
+        copy_s = (time.perf_counter() - c0) / 3
+        if world > 1:
+            tt = torch.tensor([copy_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            copy_s = float(tt[0])
+        h2d_ceiling_gbs = raw_bytes * world / copy_s / 1e9
+        del d_land
 
         def e2e_step() -> int:
-            inflight, total_hits = [], 0
+            inflight = []
             def collect_one():
                 tk, first, cnt = inflight.pop(0)
                 ctx.collect(tk, None, h_masks[first:first + cnt], h_counts[first:first + cnt],
@@ -533,14 +692,66 @@ def main() -> None:
             tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_s = float(tt[0])
-        d2h = n_spectra * (4 + 4 * words + 16 * 8)
-        e2e = {"value": total_samples * e2e_steps / e2e_s / 1e6, "unit": UNIT,
+        # no hit record was dropped: the cap holds for every spectrum of the batch (the C++ host re-runs a spectrum
+        # that overflows, process.cpp; this leg has no such fallback, so it must not need one)
+        max_hits = int(h_counts.max())
+        if max_hits > HIT_CAP:
+            raise SystemExit(f"bench.py: a spectrum has {max_hits} hits > record capacity {HIT_CAP}: e2e leg would drop hits")
+        same_as_device = int(h_counts.sum()) == int(d_count.to(torch.int64).sum())
+        d2h = n_spectra * (4 + 4 * words + HIT_CAP * 8)
+        e2e_value = total_samples * e2e_steps / e2e_s / 1e6
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": int(raw_bytes), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": e2e_s / e2e_steps * 1e3,
                "path": "scn_submit/scn_collect, pinned host raw buffers, 3 ticket slots x %d spectra; "
-                       "D2H = hit counts + masks + <=16 hit records per spectrum; dB spectrum stays in HBM" % e2e_chunk,
-               "hits_per_step": e2e_hits}
+                       "D2H = hit counts + masks + <=%d hit records per spectrum; dB spectrum stays in HBM" % (e2e_chunk, HIT_CAP),
+               "hits_per_step": e2e_hits, "max_hits_in_a_spectrum": max_hits, "hit_total_equals_device_path": same_as_device,
+               "h2d_gbs": raw_bytes * world * e2e_steps / e2e_s / 1e9,
+               "h2d_ceiling_gbs": h2d_ceiling_gbs,
+               "h2d_ceiling_note": "bare pinned-host -> device copies of the same chunks on 3 streams, all ranks at "
+                                   "once, max over ranks: the PCIe/host roofline of this leg",
+               "frac_of_h2d_ceiling": (raw_bytes * world * e2e_steps / e2e_s / 1e9) / h2d_ceiling_gbs}
         B.free_pinned(host_addr)
+
+    # ---- N = 1 extras: the other BASELINE configs kernel-only, a sustained-clock loop, the plugin surface ---------
+    per_config = sustained = plugin = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del d_spec
+        torch.cuda.empty_cache()
+        rows = []
+        for name in ("cfg1", "cfg3", "cfg4"):
+            w_ = WORKLOADS[name]
+            r = kernel_only(torch, S, w_["kind"], w_["n"], w_["K"], w_["dc"], w_["win"], w_["enob"], local_rank, peak)
+            r["config"] = name
+            rows.append(r)
+        for n_ in (256, 1024, 4096, 8192, 16384, 65536):
+            for kind_, dc_, enob_ in ((1, True, 8), (4, False, 0)):
+                r = kernel_only(torch, S, kind_, n_, 1, dc_, 5, enob_, local_rank, peak)
+                r["config"] = "cfg5 sweep"
+                rows.append(r)
+        per_config = rows
+        # sustained: the headline kernel back to back for >= sustain-seconds with the SM clock / power sampled
+        d_spec = torch.empty((n_spectra, n), dtype=torch.float32, device=dev) if spectrum else None
+        s2 = ClockSampler(nvml_index(torch, local_rank))
+        reps = max(10, int(args.sustain_seconds * 1e3 / kern_ms_rank))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        torch.cuda.synchronize()
+        s2.start()
+        evs[0].record(stream)
+        for i in range(reps):
+            ctx.launch_device(raw.data_ptr(), n_spectra, d_spec.data_ptr() if spectrum else 0, d_mask.data_ptr(),
+                              d_count.data_ptr(), 0, 0, sh)
+            evs[i + 1].record(stream)
+        torch.cuda.synchronize()
+        c2 = s2.stop()
+        ts = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)])
+        q = max(1, reps // 4)
+        sustained = {"seconds": float(ts.sum() / 1e3), "launches": reps,
+                     "msamples_per_s": samples_per_rank / ts.mean() / 1e3,
+                     "first_quarter_msamples_per_s": samples_per_rank / ts[:q].mean() / 1e3,
+                     "last_quarter_msamples_per_s": samples_per_rank / ts[-q:].mean() / 1e3,
+                     "clocks": c2}
+        plugin = plugin_surface(wl)
 
     if rank == 0:
         cpu = None
@@ -555,18 +766,23 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "fft_size": n, "averaging": K,
-                       "retune_steps": n_steps, "buffers_per_step_per_gpu": spectra_per_step_per_gpu * K,
-                       "samples_per_gpu_per_step": samples_per_rank, "input_bytes_per_gpu": int(raw_bytes),
-                       "l2_policy": "inputs_larger_than_l2" if raw_bytes > (126 << 20) else "inputs_fit_l2",
-                       "sharding": "contiguous (retune step, buffer) units per rank; NCCL all-gather of "
-                                   "per-step records" if world > 1 else "single GPU",
-                       "threshold_db": thr, "spectrum_written": spectrum},
+            "config": workload_config(args.workload, wl, spectrum, n_steps),
+            "run": {"buffers_per_step_per_gpu": spectra_per_step_per_gpu * K,
+                    "samples_per_gpu_per_step": samples_per_rank, "input_bytes_per_gpu": int(raw_bytes),
+                    "l2_policy": "inputs_larger_than_l2" if raw_bytes > (126 << 20) else "inputs_fit_l2",
+                    "sharding": ("contiguous (retune step, buffer) units per rank; per-step records exchanged over "
+                                 + ("NVLink peer-memory windows (scn_exchange: publish(i) + merge(i-1), no rendezvous)"
+                                    if xch is not None else "an NCCL all-gather on a side stream")) if world > 1 else "single GPU",
+                    "threshold_db": thr},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_2_threads": cpu2, "cpu_fft_only_upper_bound": cpu_fft,
-            "parity": parity, "step_ms": step_ms,
+            "parity": parity, "records_check": records_check, "step_ms": step_ms,
+            "per_config": per_config, "sustained": sustained, "plugin_e2e": plugin,
         }
         print(json.dumps(line), flush=True)
+    if xch is not None:
+        barrier()
+        xch.close()
     if world > 1:
         dist.destroy_process_group()
 

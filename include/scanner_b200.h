@@ -183,6 +183,34 @@ SCN_API int scn_summarize_steps(scn_ctx* ctx, const uint32_t* d_hit_mask, const 
 SCN_API int scn_merge_step_records(scn_ctx* ctx, const uint32_t* d_parts, uint32_t n_parts,
                                    uint32_t n_steps, uint32_t* d_out, void* stream);
 
+/* ---- Record exchange between the GPUs of one box over NVLink peer memory (scn_exchange.cu) ----------------
+ * The alternative to all-gathering scn_summarize_steps' partial records with NCCL: every rank owns a window in
+ * its HBM that its peers write directly (peer-mapped stores + a flag), so no rank ever waits at a rendezvous
+ * and no collective kernel competes with the persistent fused kernel for an SM.
+ *   create  -> one window per rank (device = CUDA ordinal; record_words = scn_record_words())
+ *   handle / connect_ipc   : ranks in different processes swap the 64-byte CUDA IPC handles (bench.py does it
+ *                            with torch.distributed) and map each other's windows
+ *   connect_local          : ranks that are devices of ONE process (csrc/host/sweepProcessor.cpp)
+ *   publish(d_records)     : stores this rank's [n_steps][record_words] partial records into every peer's
+ *                            window; returns the sequence number (1, 2, ...) of the batch
+ *   merge(seq, d_merged)   : waits (device side, bounded ~10 s) until every rank has published `seq`, then
+ *                            writes the merged records (sum of words 0,1; OR of the mask words)
+ * Contract: every rank merges every sequence number and issues merge(s) before publish(s + 2) on the same
+ * stream (publish(i) then merge(i - 1) per batch is the intended use: ranks never wait for each other).
+ * scn_exchange_status reports a merge that gave up waiting (0 = none). */
+#define SCN_IPC_HANDLE_BYTES 64
+typedef struct scn_exchange scn_exchange;
+SCN_API int scn_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t n_steps,
+                                uint32_t record_words, scn_exchange** out);
+SCN_API int scn_exchange_handle(scn_exchange* x, unsigned char* handle /* [SCN_IPC_HANDLE_BYTES] */);
+SCN_API int scn_exchange_connect_ipc(scn_exchange* x, const unsigned char* handles /* [world][SCN_IPC_HANDLE_BYTES] */);
+SCN_API int scn_exchange_connect_local(scn_exchange* const* all /* [world], index == rank */, uint32_t world);
+SCN_API int scn_exchange_publish(scn_exchange* x, const uint32_t* d_records, void* stream, uint64_t* seq_out);
+SCN_API int scn_exchange_merge(scn_exchange* x, uint64_t seq, uint32_t* d_merged, void* stream);
+SCN_API int scn_exchange_status(scn_exchange* x, uint32_t* timed_out_seq);
+SCN_API uint32_t scn_exchange_slots(void);
+SCN_API int scn_exchange_destroy(scn_exchange* x);
+
 /* ---- Standalone sample conversion (replaces Utility::*_to_float_complex, utility.cpp:9-84, as called by
  * MessageQueue::AppendSamples, messageQueue.h:190-237) -------------------------------------------------
  * raw: n_buffers buffers of the context's sample kind; out: n_buffers * sample_count fftwf_complex

@@ -11,6 +11,6 @@ from .binding import (  # noqa: F401
     MODE_TIME_DOMAIN, MODE_FREQUENCY_DOMAIN, OUT_SPECTRUM, OUT_HITS,
     ScannerError, SpectrumSense, lib, lib_path, hit_dtype,
     use_window, hit_frequency, frequency_table, window_build, shard_steps,
-    bytes_per_sample,
+    bytes_per_sample, RecordExchange,
 )
-from .sweep import ShardPlan, plan_shard, gather_step_records  # noqa: F401,E402
+from .sweep import ShardPlan, plan_shard, gather_step_records, open_record_exchange  # noqa: F401,E402

@@ -72,6 +72,15 @@ SYMBOLS = [
     ("scn_record_words", _U32, [_VP]),
     ("scn_summarize_steps", _I, [_VP, _VP, _VP, _U32, _U64, _U32, _U32, _VP, _VP]),
     ("scn_merge_step_records", _I, [_VP, _VP, _U32, _U32, _VP, _VP]),
+    ("scn_exchange_create", _I, [_I, _U32, _U32, _U32, _U32, C.POINTER(_VP)]),
+    ("scn_exchange_handle", _I, [_VP, _VP]),
+    ("scn_exchange_connect_ipc", _I, [_VP, _VP]),
+    ("scn_exchange_connect_local", _I, [C.POINTER(_VP), _U32]),
+    ("scn_exchange_publish", _I, [_VP, _VP, _VP, C.POINTER(_U64)]),
+    ("scn_exchange_merge", _I, [_VP, _U64, _VP, _VP]),
+    ("scn_exchange_status", _I, [_VP, C.POINTER(_U32)]),
+    ("scn_exchange_slots", _U32, []),
+    ("scn_exchange_destroy", _I, [_VP]),
     ("scn_hackrf_prepass_device", _I, [_VP, _VP, _U32, _U32, _VP, _VP, _VP]),
     ("scn_convert_device", _I, [_VP, _VP, _U32, _VP, _VP]),
     ("scn_convert_host", _I, [_VP, _VP, _U32, _VP]),
@@ -298,6 +307,60 @@ class SpectrumSense:
     @property
     def record_words(self) -> int:
         return self.words + 2
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class RecordExchange:
+    """One scn_exchange: this rank's window for the NVLink peer-memory exchange of per-step records."""
+
+    def __init__(self, device: int, rank: int, world: int, n_steps: int, record_words: int):
+        self._lib = lib()
+        self.rank, self.world = rank, world
+        h = _VP()
+        _check(self._lib.scn_exchange_create(device, rank, world, n_steps, record_words, C.byref(h)))
+        self._x = h
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(self._lib.scn_exchange_handle(self._x, C.cast(buf, _VP)))
+        return bytes(buf)
+
+    def connect_ipc(self, handles: list[bytes]) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == IPC_HANDLE_BYTES * self.world
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self._lib.scn_exchange_connect_ipc(self._x, C.cast(buf, _VP)))
+
+    @staticmethod
+    def connect_local(exchanges: "list[RecordExchange]") -> None:
+        arr = (_VP * len(exchanges))(*[e._x for e in exchanges])
+        _check(lib().scn_exchange_connect_local(arr, len(exchanges)))
+
+    def publish(self, d_records: int, stream: int = 0) -> int:
+        seq = _U64(0)
+        _check(self._lib.scn_exchange_publish(self._x, _VP(d_records), _VP(stream or None), C.byref(seq)))
+        return int(seq.value)
+
+    def merge(self, seq: int, d_merged: int, stream: int = 0) -> None:
+        _check(self._lib.scn_exchange_merge(self._x, seq, _VP(d_merged), _VP(stream or None)))
+
+    def status(self) -> int:
+        v = _U32(0)
+        _check(self._lib.scn_exchange_status(self._x, C.byref(v)))
+        return int(v.value)
+
+    def close(self) -> None:
+        if getattr(self, "_x", None):
+            self._lib.scn_exchange_destroy(self._x)
+            self._x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def alloc_pinned(nbytes: int) -> tuple[int, np.ndarray]:

@@ -52,6 +52,23 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace scn {
+// error text for the other translation units of the C ABI (scn_exchange.cu)
+int api_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+}  // namespace scn
+
+namespace {
+
 #define SCN_CUDA(expr)                                                                  \
   do {                                                                                  \
     cudaError_t e_ = (expr);                                                            \
@@ -118,6 +135,9 @@ struct scn_ctx {
   float* d_p = nullptr;          // power [chunk spectra][16][N2]
   int2* d_dcs = nullptr;         // per-buffer dc
   uint32_t chunk_spectra = 0;
+  // work counters of the persistent kernels (scn::WorkQueue): one per launch, rotated, self-resetting
+  uint32_t* d_work = nullptr;
+  uint32_t work_next = 0;
   std::vector<Slot> slots;
   uint32_t next_slot = 0;
   uint64_t launches = 0;
@@ -128,6 +148,14 @@ struct scn_ctx {
 };
 
 namespace {
+
+constexpr uint32_t kWorkCounters = 64;      // launches of one context that may be in flight at once
+constexpr uint32_t kWorkStride = 8;         // uint32 words between counters (one 32-byte sector each)
+uint32_t* next_work_counter(scn_ctx* c) {
+  uint32_t* w = c->d_work + size_t(c->work_next % kWorkCounters) * kWorkStride;
+  c->work_next++;
+  return w;
+}
 
 int ilog2_exact(uint32_t n) {
   if (n == 0 || (n & (n - 1))) return -1;
@@ -222,6 +250,7 @@ int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d
   p.use_window = c->cfg.use_window;
   p.dc_ignore = c->cfg.dc_ignore_window;
   p.win_mirror = c->win_mirror ? 1u : 0u;
+  p.work = next_work_counter(c);
   const uint32_t F = uint32_t(c->variant.transforms_per_cta);
   const uint32_t n_groups = (n_spectra + F - 1) / F;
   uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
@@ -246,6 +275,7 @@ int launch_rows(scn_ctx* c, const void* d_y, uint32_t n_rows, float* d_power, cu
   p.inv_averaging = 1.0f / float(c->K);
   p.rpb_shift = 4;
   p.power_out = d_power;
+  p.work = next_work_counter(c);
   const uint32_t F = uint32_t(c->variant.transforms_per_cta);
   const uint32_t n_groups = (n_rows + F - 1) / F;
   uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
@@ -429,6 +459,9 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     cudaFuncAttributes fa{};
     if (cudaFuncGetAttributes(&fa, c->variant.func) == cudaSuccess) c->regs = fa.numRegs;
 
+    e = cudaMalloc(&c->d_work, sizeof(uint32_t) * kWorkCounters * kWorkStride);
+    if (e == cudaSuccess) e = cudaMemset(c->d_work, 0, sizeof(uint32_t) * kWorkCounters * kWorkStride);
+    if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "work counter allocation failed: %s", cudaGetErrorString(e)));
     // Window taps, with the converter's power-of-two scale folded in (exact).
     std::vector<float> w(cf.sample_count);
     const float s = (cf.sample_kind == SCN_KIND_FLOAT_COMPLEX) ? 1.0f : c->onebymax;
@@ -494,6 +527,7 @@ SCN_API int scn_destroy(scn_ctx* c) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     free_slot(s);
   }
+  if (c->d_work) cudaFree(c->d_work);
   if (c->d_window) cudaFree(c->d_window);
   if (c->d_twiddles) cudaFree(c->d_twiddles);
   if (c->d_ones) cudaFree(c->d_ones);

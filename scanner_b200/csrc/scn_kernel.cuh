@@ -71,6 +71,26 @@ struct KernelParams {
   // 1 when window[n] == window[N-1-n] bit for bit (every gr-fft window is): kernels whose tables overflow L1
   // (scn_p64.cuh at N = 8192) then read taps n >= N/2 from the mirrored address, halving the table footprint.
   uint32_t win_mirror;
+  // Work counter of this launch (WorkQueue below): [0] tiles handed out beyond the static ones, [1] takers retired.
+  uint32_t* __restrict__ work;
+};
+
+// Dynamic tile distribution for the persistent kernels.  A "taker" (a warp in scn_wpt.cuh, a CTA elsewhere) owns
+// tiles taker, taker + takers statically -- so its first loads need no round trip -- and takes every later tile
+// from one global counter, one tile AHEAD of the loads that need the index (the atomic's latency hides behind a
+// transform).  Why: with a static stride a CTA that starts late or shares its SM with another kernel (the NCCL
+// all-gather of the previous batch's records, bench.py) delays the whole launch by its entire share; with the
+// counter it simply takes fewer tiles.  The last taker to retire zeroes both words, so the counter needs no reset
+// between launches; a context rotates over several counters so launches on different streams never share one.
+struct WorkQueue {
+  uint32_t* w;
+  uint32_t takers;
+  __device__ __forceinline__ WorkQueue(uint32_t* work, uint32_t n_takers) : w(work), takers(n_takers) {}
+  __device__ __forceinline__ uint32_t take() { return 2u * takers + atomicAdd(w, 1u); }
+  // called once per taker, after its last take() has returned
+  __device__ __forceinline__ void retire() {
+    if (atomicAdd(w + 1, 1u) == takers - 1u) { atomicExch(w, 0u); atomicExch(w + 1, 0u); }
+  }
 };
 
 // dB = 10*log2(sqrt(p))/log2(10) = (5/log2(10)) * log2(p)
@@ -104,7 +124,8 @@ struct Geometry {
   static constexpr size_t kMaskBytes = sizeof(uint32_t) * size_t(WORDS) * F * 2;   // ping-pong by spectrum parity
   static constexpr int RED_SLOTS = (WARPS > F) ? WARPS : F;                        // (si, sq) pairs per parity
   static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * RED_SLOTS * 2;         // ping-pong by tile parity
-  static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes;
+  static constexpr size_t kWorkBytes = 16;                                         // next-group index, ping-pong
+  static constexpr size_t kSmemBytes = kXchBytes + kMaskBytes + kRedBytes + kWorkBytes;
   // register budget: 128/thread up to 512-thread CTAs
 // (resident-CTA target per kernel variant: see min_ctas() below)
 };
@@ -302,6 +323,7 @@ spectrum_sense_kernel(const KernelParams p) {
   float2* xch_all = reinterpret_cast<float2*>(smem_raw);
   uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + G::kXchBytes);          // [2][F][WORDS]
   int32_t* sred = reinterpret_cast<int32_t*>(smem_raw + G::kXchBytes + G::kMaskBytes);   // [2][RED_SLOTS][2]
+  uint32_t* swork = reinterpret_cast<uint32_t*>(smem_raw + G::kXchBytes + G::kMaskBytes + G::kRedBytes);   // [2]
 
   const int tid = threadIdx.x;
   const int f = tid / T;             // which resident transform
@@ -338,9 +360,14 @@ spectrum_sense_kernel(const KernelParams p) {
     candbits |= (cand ? 1u : 0u) << q;
   }
 
-  // ---- tile stream of this CTA: (group, k) for group = blockIdx.x, +gridDim.x, ...; k = 0..K-1 ----
-  uint32_t g = blockIdx.x;
-  if (g >= n_groups) return;
+  // ---- tile stream of this CTA: (group, k), k = 0..K-1; groups blockIdx.x and blockIdx.x + gridDim.x are
+  // static, later ones come from the launch's work counter (WorkQueue above; row mode keeps the static stride) ----
+  WorkQueue wq(p.work, gridDim.x);
+  uint32_t g = blockIdx.x, g_after = blockIdx.x + gridDim.x, g_after2 = 0;
+  if (g >= n_groups) {
+    if (!ROWS && tid == 0) wq.retire();
+    return;
+  }
   uint32_t k = 0;
   uint32_t xsel = 0;      // ping-pong selector of the exchange tile
   uint32_t tpar = 0;      // tile parity (DC partial sums ping-pong)
@@ -435,8 +462,11 @@ spectrum_sense_kernel(const KernelParams p) {
     const bool cur_live = live;
     const uint32_t cur_g = g, cur_k = k;
     uint32_t ng = g, nk = k + 1;
-    if (nk == K) { nk = 0; ng = g + gridDim.x; }
+    if (nk == K) { nk = 0; ng = g_after; }
     const bool has_next = ng < n_groups;
+    if constexpr (!ROWS) {
+      if (cur_k == 0 && tid == 0) swork[spar] = wq.take();   // the group after g_after; read behind the epilogue barrier
+    }
     bool next_live = false;
     if (has_next) {
       const uint8_t* nbuf = tile_ptr(ng, nk, next_live);
@@ -563,6 +593,7 @@ spectrum_sense_kernel(const KernelParams p) {
         if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); }
       }
       __syncthreads();
+      g_after2 = swork[spar];
       if constexpr (kDC) {
         if (has_next) { finish_dc(sred + tpar * (2 * G::RED_SLOTS), ndci, ndcq); tpar ^= 1u; }
       }
@@ -617,8 +648,10 @@ spectrum_sense_kernel(const KernelParams p) {
     }
 
     if (!has_next) break;
+    if (nk == 0) g_after = ROWS ? g_after + gridDim.x : g_after2;
     g = ng; k = nk; live = next_live; dci = ndci; dcq = ndcq;
   }
+  if (!ROWS && tid == 0) wq.retire();
 #undef SCN_TWIDDLE_PREP
 #undef SCN_TWIDDLE_APPLY
 }

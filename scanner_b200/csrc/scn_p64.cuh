@@ -34,13 +34,14 @@ struct P64Geometry {
   static constexpr size_t kTileBytes = sizeof(float2) * size_t(TILE_ELEMS);
   static constexpr size_t kMaskBytes = sizeof(uint32_t) * WORDS * 2;          // ping-pong by spectrum parity
   static constexpr size_t kRedBytes = sizeof(int32_t) * 2 * WARPS * 2;        // DC partials, ping-pong
-  static constexpr size_t kStageOffset = kTileBytes + kMaskBytes + kRedBytes + 16;   // + mbarrier slot
+  static constexpr size_t kWorkBytes = 16;                                    // next-spectrum index, ping-pong
+  static constexpr size_t kStageOffset = kTileBytes + kMaskBytes + kWorkBytes + kRedBytes + 16;   // + mbarrier slot
   static_assert(kStageOffset % 16 == 0, "staging buffer must be 16-byte aligned for the bulk copy");
 };
 template <int LOG2N, int KIND>
 constexpr size_t p64_smem_bytes() {
   using G = P64Geometry<LOG2N>;
-  return KIND == SCN_KIND_FLOAT_COMPLEX ? G::kTileBytes + G::kMaskBytes
+  return KIND == SCN_KIND_FLOAT_COMPLEX ? G::kStageOffset      // tile | masks | work | (red) | mbarrier
                                         : G::kStageOffset + size_t(G::N) * KindTraits<KIND>::kBytes;
 }
 // twiddle tables (host: scn_api.cu, layout 2): twA[(r-1)*64 + k] = exp(-2 pi i k r / 4096), r = 1..63, k < 64;
@@ -71,8 +72,9 @@ spectrum_sense_p64_kernel(const KernelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + G::kTileBytes);                      // [2][WORDS]
-  int32_t* sred = reinterpret_cast<int32_t*>(smem_raw + G::kTileBytes + G::kMaskBytes);        // [2][WARPS][2]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::kTileBytes + G::kMaskBytes + G::kRedBytes);
+  uint32_t* swork = reinterpret_cast<uint32_t*>(smem_raw + G::kTileBytes + G::kMaskBytes);     // [2]
+  int32_t* sred = reinterpret_cast<int32_t*>(smem_raw + G::kTileBytes + G::kMaskBytes + G::kWorkBytes);   // [2][WARPS][2]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::kTileBytes + G::kMaskBytes + G::kWorkBytes + G::kRedBytes);
   const unsigned char* stage = smem_raw + G::kStageOffset;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t half = N / 2;
@@ -123,9 +125,14 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     odcq = int(unsigned(sq) >> LOG2N);
   };
 
-  // ---- tile stream of this CTA: (spectrum, k), spectrum = blockIdx.x, +gridDim.x, ...; k = 0..K-1 ----
-  uint32_t s = blockIdx.x, k = 0;
-  if (s >= p.n_spectra) return;
+  // ---- tile stream of this CTA: (spectrum, k), k = 0..K-1; spectra blockIdx.x and blockIdx.x + gridDim.x are
+  // static, later ones come from the launch's work counter (WorkQueue, scn_kernel.cuh) ----
+  WorkQueue wq(p.work, gridDim.x);
+  uint32_t s = blockIdx.x, s_after = blockIdx.x + gridDim.x, s_after2 = 0, k = 0;
+  if (s >= p.n_spectra) {
+    if (t == 0) wq.retire();
+    return;
+  }
   if constexpr (kStaged) {
     if (t == 0) {
       mbar_init(bar, 1);
@@ -150,7 +157,32 @@ spectrum_sense_p64_kernel(const KernelParams p) {
 #ifndef SCN_P64_PREFETCH
 #define SCN_P64_PREFETCH 1
 #endif
-  constexpr bool kPrefetch = SCN_P64_PREFETCH && !kStaged && !AVG;
+  // fp32 IQ, SCN_P64_LAND: the exchange tile doubles as the landing zone of ONE TMA bulk copy of the next raw
+  // buffer (32 / 64 KB), issued by one thread as soon as every thread has finished its last gather from the tile
+  // (N = 4096: before the second radix-64, so the copy overlaps half of the transform and the whole epilogue;
+  // N = 8192: before the epilogue).  Threads then read their column with LDS.  The raw stream no longer passes
+  // through L1 (the window / twiddle tables stay resident) and no registers are tied up by a prefetch.
+#ifndef SCN_P64_LAND
+#define SCN_P64_LAND 1
+#endif
+  constexpr bool kLand = SCN_P64_LAND && !kStaged;
+  if constexpr (kLand) {
+    if (t == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, kRawBytes);
+      bulk_g2s(tile, p.raw + size_t(s) * K * kRawBytes, kRawBytes, bar);
+    }
+    __syncthreads();
+  }
+  auto land_next = [&](bool has_next, uint32_t ns, uint32_t nk) {
+    // every thread has passed a barrier after its last read of the tile
+    if (has_next && t == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, kRawBytes);
+      bulk_g2s(tile, p.raw + (size_t(ns) * K + nk) * kRawBytes, kRawBytes, bar);
+    }
+  };
+  constexpr bool kPrefetch = SCN_P64_PREFETCH && !kStaged && !AVG && !kLand;
 #ifndef SCN_P64_PREFETCH_13
 #define SCN_P64_PREFETCH_13 16
 #endif
@@ -165,14 +197,27 @@ spectrum_sense_p64_kernel(const KernelParams p) {
   float acc[AVG ? 64 : 1];
   while (true) {
     uint32_t ns = s, nk = k + 1;
-    if (nk == K) { nk = 0; ns = s + gridDim.x; }
+    if (nk == K) { nk = 0; ns = s_after; }
     const bool has_next = ns < p.n_spectra;
+    if (k == 0 && t == 0) swork[spar] = wq.take();     // the spectrum after s_after; read behind the epilogue barrier
     const bool epilogue_tile = (k == K - 1);
     const size_t buf_index = size_t(s) * K + k;
 
     // ---- load / convert + window ----------------------------------------------------------------------------
     float2 v[64];
-    if constexpr (!kStaged) {
+    if constexpr (kLand) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      const float2* land = tile + t;
+#pragma unroll
+      for (int r = 0; r < 64; r++) v[r] = land[T * r];
+#pragma unroll
+      for (int r = 0; r < 64; r++) {
+        const float w = wtap(r);
+        v[r] = __fmul2_rn(v[r], make_float2(w, w));
+      }
+      __syncthreads();                                 // every column is in registers: the tile may be scattered into
+    } else if constexpr (!kStaged) {
       const float2* src = reinterpret_cast<const float2*>(p.raw) + buf_index * N + t;
 #pragma unroll
       for (int r = 0; r < 64; r++) v[r] = (kPrefetch && r < kPre) ? nxt[r] : ldg_stream(src + T * r);
@@ -227,6 +272,10 @@ spectrum_sense_p64_kernel(const KernelParams p) {
 #pragma unroll
       for (int r = 0; r < 64; r++) v[r] = base[GSTRIDE * r];
     }
+    if constexpr (kLand && LOG2N == 12) {
+      __syncthreads();                                 // last gather done: the tile is free for the next raw buffer
+      land_next(has_next, ns, nk);
+    }
     const int kk = t & 63;
     {
       const float2* tw = twA + kk;
@@ -263,6 +312,10 @@ spectrum_sense_p64_kernel(const KernelParams p) {
         v[32 + c] = csub(a0, b0);                      // bin t + 128 (c + 32)
         v[16 + c] = add_mi(a1, b1);                    // bin t + 128 (c + 16)
         v[48 + c] = sub_mi(a1, b1);                    // bin t + 128 (c + 48)
+      }
+      if constexpr (kLand) {
+        __syncthreads();                               // last read of the tile done: land the next raw buffer in it
+        land_next(has_next, ns, nk);
       }
     }
 
@@ -348,6 +401,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
         }
       }
       __syncthreads();
+      s_after2 = swork[spar];
       if constexpr (kDC) {
         if (has_next) { finish_dc(sred + 2 * G::WARPS * tpar, dci, dcq); tpar ^= 1u; }
       }
@@ -394,8 +448,10 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     }
 
     if (!has_next) break;
+    if (nk == 0) s_after = s_after2;
     s = ns; k = nk;
   }
+  if (t == 0) wq.retire();
 }
 
 }  // namespace scn

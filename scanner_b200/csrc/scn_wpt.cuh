@@ -20,18 +20,12 @@ constexpr int kWptN = 2048;
 constexpr int kWptWarpsPerCta = 2;
 // tile padding: 1 float2 per 64 -> lane stride 65 elements: conflict-free 64-bit scatter, unit-stride gather
 __host__ __device__ constexpr int wpt_tile_elems() { return kWptN + (kWptN / 64); }
-// Raw staging: the next transform's 4 KB of int8 IQ is fetched by ONE bulk async copy (TMA,
-// cp.async.bulk + mbarrier complete_tx) into a warp-private shared-memory buffer while the current
-// transform is in the FFT; no registers are tied up by the prefetch.
-// Measured on B200 (profiles/README.md): staging costs 32 extra LDS per lane per transform and the
-// tighter register allocation schedules worse -- 405 vs 450 Gsamples/s -- so the default prefetches
-// into 32 registers right after the conversion (issuing them later, after the pass-0 scatter when the
-// register file is nearly empty, measured 423); the TMA path stays as a build option.
-#ifndef SCN_WPT_TMA
-#define SCN_WPT_TMA 0
-#endif
-constexpr size_t kWptRawBytes = size_t(kWptN) * 2;
-constexpr size_t kWptWarpBytes = sizeof(float2) * size_t(wpt_tile_elems()) + (SCN_WPT_TMA ? kWptRawBytes + 16 : 0);
+// The next transform's 4 KB of int8 IQ is prefetched into 32 registers right after the conversion.  Measured
+// alternatives on B200 (profiles/README.md), all removed: staging it with one TMA bulk copy per transform
+// (405 vs 450 Gsamples/s: 32 extra LDS per lane and a tighter register allocation), issuing the loads after the
+// pass-0 scatter (423), keeping the two warps of a CTA in lockstep for the instruction cache (+0.7 %, noise),
+// 5-6 CTAs per SM at 168 registers (371).
+constexpr size_t kWptWarpBytes = sizeof(float2) * size_t(wpt_tile_elems());
 static_assert(kWptWarpBytes % 16 == 0, "warp region must keep 16-byte alignment");
 constexpr size_t kWptSmemBytes = kWptWarpBytes * kWptWarpsPerCta;
 
@@ -134,25 +128,17 @@ __device__ __forceinline__ void dft64_inplace(float2 (&v)[64]) {
 __host__ __device__ constexpr int dft64_out_index(int slot) { return (slot >> 3) + 8 * (slot & 7); }
 
 // Twiddle table for this variant: tww[(r-1) * 32 + lane] = exp(-2 pi i lane r / 2048), r = 1..63 (host: scn_api.cu).
-template <bool DC>
 #ifndef SCN_WPT_MINCTAS
 #define SCN_WPT_MINCTAS 4
 #endif
+template <bool DC>
 __global__ void __launch_bounds__(32 * kWptWarpsPerCta, SCN_WPT_MINCTAS)
 spectrum_sense_wpt_kernel(const KernelParams p) {
   constexpr int N = kWptN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-#if !SCN_WPT_TMA
   float2* tile = reinterpret_cast<float2*>(smem_raw) + size_t(warp) * wpt_tile_elems();
-#else
-  unsigned char* wbase = smem_raw + size_t(warp) * kWptWarpBytes;
-  float2* tile = reinterpret_cast<float2*>(wbase);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(wbase + sizeof(float2) * size_t(wpt_tile_elems()));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + sizeof(float2) * size_t(wpt_tile_elems()) + kWptRawBytes);
-  uint32_t phase = 0;
-#endif
   const uint32_t half = N / 2;
   const uint32_t gw = blockIdx.x * kWptWarpsPerCta + warp;          // global warp id
   const uint32_t nw = gridDim.x * kWptWarpsPerCta;
@@ -162,51 +148,20 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     const uint32_t i = j ^ half;
     return !(j < p.dc_ignore || (N - j) < p.dc_ignore) && !(i < (half - p.use_window) || i > (half + p.use_window));
   };
+  // Transform indices: the first two of a warp are static (gw, gw + nw); every later one comes from the launch's
+  // work counter (WorkQueue, scn_kernel.cuh), fetched one transform ahead of its loads so the atomic's latency
+  // hides behind an FFT.  A warp that starts late or runs slowly (another kernel holding its SM) just takes fewer.
+  WorkQueue wq(p.work, nw);
   uint32_t raw[32];                                                  // row r: samples 2*lane, 2*lane+1 (+ 64 r)
-  uint32_t s_cur = gw;
-  // EXPERIMENT, default off, not yet measured: ncu shows no_instruction stalls (0.43 warps per issue) -- the 41 KB
-  // loop body misses the L0 instruction cache while the two warps of a scheduler drift apart.  SCN_WPT_PAIRSYNC=1
-  // keeps the warps of a CTA on the same transform index with one CTA barrier per transform, so they fetch
-  // the same instructions.  Every warp of the CTA arrives the same number of times: iterations of warp 0.
-#ifndef SCN_WPT_PAIRSYNC
-#define SCN_WPT_PAIRSYNC 0
-#endif
-#if SCN_WPT_PAIRSYNC
-  const uint32_t gw0 = blockIdx.x * kWptWarpsPerCta;
-  uint32_t pair_iters = gw0 < p.n_spectra ? (p.n_spectra - gw0 + nw - 1) / nw : 0u;   // warp 0 runs the most
-  if (s_cur >= p.n_spectra) {
-    for (; pair_iters; pair_iters--) __syncthreads();
-    return;
-  }
-#else
-  if (s_cur >= p.n_spectra) return;
-#endif
-#if SCN_WPT_TMA
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, uint32_t(kWptRawBytes));
-    bulk_g2s(stage, p.raw + size_t(s_cur) * kWptRawBytes, uint32_t(kWptRawBytes), bar);
-  }
-  __syncwarp();
-#else
+  uint32_t s_cur = gw, s_next = gw + nw;
+  if (s_cur >= p.n_spectra) { if (lane == 0) wq.retire(); return; }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_cur) * N * 2) + lane;
 #pragma unroll
     for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
   }
-#endif
 
   while (true) {
-#if SCN_WPT_PAIRSYNC
-    __syncthreads();
-    pair_iters--;
-#endif
-#if SCN_WPT_TMA
-    mbar_wait(bar, phase);                        // this transform's bytes have landed
-    phase ^= 1u;
-#pragma unroll
-    for (int r = 0; r < 32; r++) raw[r] = stage[lane + 32 * r];
-#endif
     // ---- DC (warp-local), convert + window ---------------------------------------------------------------
     float2 negc = make_float2(-(kMagic + 128.0f), -(kMagic + 128.0f));
     if constexpr (DC) {
@@ -232,23 +187,15 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
       v[r] = __fmul2_rn(__fadd2_rn(a, negc), make_float2(w2.x, w2.x));          // column 0, row r
       v[32 + r] = __fmul2_rn(__fadd2_rn(b, negc), make_float2(w2.y, w2.y));     // column 1, row r
     }
-    // ---- next transform's loads go in flight now -------------------------------------------------------------
-    const uint32_t s_next = s_cur + nw;
+    // ---- next transform's loads go in flight now; the index after it is requested from the work counter ----------
     const bool has_next = s_next < p.n_spectra;
-#if SCN_WPT_TMA
-    __syncwarp();                                  // every lane has consumed the staged words
-    if (has_next && lane == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, uint32_t(kWptRawBytes));
-      bulk_g2s(stage, p.raw + size_t(s_next) * kWptRawBytes, uint32_t(kWptRawBytes), bar);
-    }
-#else
+    uint32_t ticket = 0;
     if (has_next) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_next) * N * 2) + lane;
 #pragma unroll
       for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
+      if (lane == 0) ticket = wq.take();
     }
-#endif
 
     // ---- pass 0: radix-32 on both columns; scatter (Stockham: butterfly j = 2 lane + c -> 32 j + q) ------------
     dft32_inplace<0>(v);
@@ -354,10 +301,9 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
 
     if (!has_next) break;
     s_cur = s_next;
+    s_next = __shfl_sync(0xffffffffu, ticket, 0);
   }
-#if SCN_WPT_PAIRSYNC
-  for (; pair_iters; pair_iters--) __syncthreads();   // a warp that ran one transform fewer still arrives
-#endif
+  if (lane == 0) wq.retire();
 }
 
 }  // namespace scn

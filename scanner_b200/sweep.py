@@ -59,3 +59,17 @@ def gather_step_records(records, world: int, out=None):
     # concatenation-shaped view: accepted by both the NCCL and the gloo backend
     dist.all_gather_into_tensor(out.view((world * records.shape[0],) + tuple(records.shape[1:])), records.contiguous())
     return out
+
+
+def open_record_exchange(device: int, rank: int, world: int, n_steps: int, record_words: int):
+    """NVLink peer-memory exchange of the per-step records (scn_exchange.cu) for one-process-per-GPU jobs: every
+    rank creates its window, the 64-byte CUDA IPC handles travel over torch.distributed (plumbing), every rank
+    maps its peers' windows.  world == 1 needs no handles."""
+    x = B.RecordExchange(device, rank, world, n_steps, record_words)
+    if world > 1:
+        import torch.distributed as dist
+        handles = [None] * world
+        dist.all_gather_object(handles, x.handle())
+        x.connect_ipc(handles)
+        dist.barrier()          # every window is mapped before anybody publishes into it
+    return x

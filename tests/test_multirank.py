@@ -1,5 +1,5 @@
 """N > 1 plumbing.  CPU: world_size-2 gloo run of the shard plan + record all-gather against a
-single-process result.  GPU (needs >= 2 devices): the same through the CUDA kernels and NCCL."""
+single-process result.  GPU (needs >= 2 devices): the same through the CUDA kernels, NCCL and the peer-memory exchange."""
 import os
 import socket
 import subprocess
@@ -51,6 +51,21 @@ if use_gpu:
         ss.merge_step_records(parts.data_ptr(), world, n_steps, d_out.data_ptr())
         torch.cuda.synchronize()
         merged = d_out.cpu().numpy().view(np.uint32)
+        # the same records through the NVLink peer-memory exchange (scn_exchange.cu, CUDA IPC windows): three
+        # batches so the slots rotate; publish(i) then merge(i - 1), as bench.py does
+        xch = S.open_record_exchange(rank, rank, world, n_steps, words + 2)
+        d_x = torch.zeros_like(d_rec)
+        for batch in range(1, 4):
+            assert xch.publish(d_rec.data_ptr()) == batch
+            if batch > 1:
+                xch.merge(batch - 1, d_x.data_ptr())
+                torch.cuda.synchronize()
+                assert np.array_equal(d_x.cpu().numpy().view(np.uint32), merged), ("exchange", rank, batch)
+        xch.merge(3, d_x.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_x.cpu().numpy().view(np.uint32), merged) and xch.status() == 0
+        dist.barrier()
+        xch.close()
 else:
     res = O.pipeline(mine, n, 20_000_000, enob, kind, True, 1, thr, window, use_w, precision=0)
     for u in range(plan.n_units):
