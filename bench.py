@@ -302,27 +302,38 @@ def calibrate_threshold(wl: dict, window: np.ndarray, use_w: int) -> float:
 
 # ---------------------------------------------------------------------------------------------
 def plugin_surface(wl: dict) -> dict:
-    """The reference-facing C++ surface end to end: a source thread -> SampleQueue::AppendSamples (raw bytes into the
-    pinned slab) -> ProcessSamples workers -> scn_submit/scn_collect, i.e. what replaces scan.cpp:211-238, driven by the
-    `scan_b200 bench` tool on this workload's buffer shape.  Host-bound by design (one memcpy per buffer on the
-    producer, like the reference's queue)."""
+    """The reference-facing C++ surface end to end: source thread(s) -> SampleQueue (raw bytes into the pinned slab) ->
+    ProcessSamples workers -> scn_submit_gather/scn_collect, i.e. what replaces scan.cpp:211-238, driven by the
+    `scan_b200 bench` tool on this workload's buffer shape.  Two operating points: the reference's own hand-off
+    (ONE producer thread, one AppendSamples call and one memcpy per buffer) and the batched hand-off (several producer
+    threads, 64 buffers per AppendSamplesBatch call = one HackRF USB transfer, hackRFSource.cpp:251-264)."""
     import re
     import subprocess
     tool = os.path.join(ROOT, "scanner_b200", "scan_b200")
     if not os.path.exists(tool):
         return {"unavailable": "scanner_b200/scan_b200 not built"}
     n, kind = wl["n"], wl["kind"]
-    total = max(20000, int(3.0e9 // n))            # ~3 Gsamples through the queue
-    cmd = [tool, "bench", str(kind), str(n), str(wl["enob"]), "1" if wl["dc"] else "0", "4096", str(total), "2"]
-    try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
-    except Exception as e:      # noqa: BLE001
-        return {"unavailable": str(e)}
-    m = re.search(r"plugin-surface throughput: ([0-9.]+) Msamples/s \((.*)\)", out.stdout)
-    if not m:
-        return {"unavailable": (out.stdout + out.stderr)[-300:]}
-    return {"value": float(m.group(1)), "unit": UNIT, "detail": m.group(2),
-            "path": "ReplaySource thread -> SampleQueue -> ProcessSamples (2 workers) -> C ABI; K=1 per-buffer detection"}
+    cores = os.cpu_count() or 1
+    producers = max(1, min(6, cores // 3))
+
+    def run(total, workers, max_batch, prod, append, linger):
+        cmd = [tool, "bench", str(kind), str(n), str(wl["enob"]), "1" if wl["dc"] else "0", "4096", str(total),
+               str(workers), str(max_batch), str(prod), str(append), str(linger)]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+        except Exception as e:      # noqa: BLE001
+            return {"unavailable": str(e)}
+        m = re.search(r"plugin-surface throughput: ([0-9.]+) Msamples/s \((.*)\)", out.stdout)
+        if not m:
+            return {"unavailable": (out.stdout + out.stderr)[-300:]}
+        return {"value": float(m.group(1)), "unit": UNIT, "detail": m.group(2)}
+    single = run(max(20000, int(3.0e9 // n)), 2, 4096, 1, 1, 0)
+    batched = run(max(20000, int(12.0e9 // n)), 2, 8192, producers, 64, 200)
+    out = dict(batched)
+    out["path"] = ("%d ReplaySource threads x AppendSamplesBatch(64 buffers) -> SampleQueue (pinned slab) -> "
+                   "ProcessSamples (2 workers, scn_submit_gather from the slab) -> C ABI; K=1 per-buffer detection" % producers)
+    out["single_producer_single_appends"] = single
+    return out
 
 
 def kernel_only(torch, S, kind: int, n: int, K: int, dc: bool, win: int, enob: int, device: int, peak: float,
@@ -439,67 +450,71 @@ def main() -> None:
                           device=local_rank, ticket_slots=3)
     words, rec_words = ctx.words, ctx.record_words
     d_spec = torch.empty((n_spectra, n), dtype=torch.float32, device=dev) if spectrum else None
-    d_mask = torch.empty((n_spectra, words), dtype=torch.int32, device=dev)
-    d_count = torch.empty((n_spectra,), dtype=torch.int32, device=dev)
+    # masks / counts are double-buffered: batch i's are summarised on the side stream while batch i+1 is computed
+    d_masks = [torch.empty((n_spectra, words), dtype=torch.int32, device=dev) for _ in range(2)]
+    d_counts = [torch.empty((n_spectra,), dtype=torch.int32, device=dev) for _ in range(2)]
+    d_mask, d_count = d_masks[0], d_counts[0]
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
     d_merged = torch.zeros((n_steps, rec_words), dtype=torch.int32, device=dev)
-    # records exchange (N > 1).  "peer": publish(i) + merge(i-1) on the main stream, both tiny kernels, no rank ever
-    # waits for another (scn_exchange.cu).  "nccl": all-gather + merge on a high-priority side stream, double-buffered.
+    # A step = the fused kernel on the main stream; everything after it -- the per-retune-step records
+    # (scn_summarize_steps) and, N > 1, their exchange -- runs on a high-priority side stream UNDER the fused kernel of
+    # the next batch:
+    #   "peer": publish(i) + merge(i-1), two tiny kernels over NVLink peer-memory windows, no rank ever waits for
+    #           another (scn_exchange.cu);   "nccl": all-gather + merge.
+    # The fused kernel hands out its tiles dynamically (WorkQueue), so the CTAs those small kernels displace at the
+    # start of a batch cost their own run time, not a whole static share of the batch.
+    # (Folding the records into the fused kernel with atomics was tried and removed: ~0.5 M atomics per batch on the
+    # 2-3 L2 lines of the current step's record cost 7 % of the kernel, and the extra code another 7 % in registers.)
     xch = None
-    d_rec = torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev)
     if world > 1 and args.exchange == "peer":
         xch = S.open_record_exchange(local_rank, rank, world, n_steps, rec_words)
-    d_recs = [d_rec, torch.empty_like(d_rec)]
+    d_recs = [torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)]
     d_gathers = [torch.empty((world, n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)] \
         if (world > 1 and xch is None) else None
-    side = torch.cuda.Stream(device=dev, priority=-1) if d_gathers is not None else None
-    rec_ready = [torch.cuda.Event() for _ in range(2)]
-    rec_free = [torch.cuda.Event() for _ in range(2)]
+    side = torch.cuda.Stream(device=dev, priority=-1)
+    out_ready = [torch.cuda.Event() for _ in range(2)]
+    out_free = [torch.cuda.Event() for _ in range(2)]
     step_no = [0]
     last_seq = [0]
 
     kernel_events = []
 
     def step(timed: bool) -> None:
+        par = step_no[0] & 1
+        step_no[0] += 1
+        if step_no[0] > 2:
+            stream.wait_event(out_free[par])                         # batch i-2's masks / counts have been summarised
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        ctx.launch_device(raw.data_ptr(), n_spectra, d_spec.data_ptr() if spectrum else 0, d_mask.data_ptr(),
-                          d_count.data_ptr(), 0, 0, sh)
+        ctx.launch_device(raw.data_ptr(), n_spectra, d_spec.data_ptr() if spectrum else 0, d_masks[par].data_ptr(),
+                          d_counts[par].data_ptr(), 0, 0, sh)
         if timed:
             e1.record(stream)
             kernel_events.append((e0, e1))
-        par = step_no[0] & 1
-        step_no[0] += 1
-        if xch is not None or world == 1:
-            ctx.summarize_steps(d_mask.data_ptr(), d_count.data_ptr(), n_spectra, first_unit, units_per_step,
-                                n_steps, d_rec.data_ptr(), sh)
-            if xch is not None:
-                seq = xch.publish(d_rec.data_ptr(), sh)
-                if seq > 1:
-                    xch.merge(seq - 1, d_merged.data_ptr(), sh)      # the previous batch: its rows landed long ago
-                last_seq[0] = seq
-            return
-        if step_no[0] > 2:
-            stream.wait_event(rec_free[par])                         # the exchange two steps ago is done with it
-        ctx.summarize_steps(d_mask.data_ptr(), d_count.data_ptr(), n_spectra, first_unit, units_per_step,
-                            n_steps, d_recs[par].data_ptr(), sh)
-        rec_ready[par].record(stream)
+        out_ready[par].record(stream)
         with torch.cuda.stream(side):
-            side.wait_event(rec_ready[par])
-            S.gather_step_records(d_recs[par], world, out=d_gathers[par])   # NCCL all-gather, ~13 KB per rank
-            ctx.merge_step_records(d_gathers[par].data_ptr(), world, n_steps, d_merged.data_ptr(),
-                                   side.cuda_stream)
-            rec_free[par].record(side)
+            side.wait_event(out_ready[par])
+            ctx.summarize_steps(d_masks[par].data_ptr(), d_counts[par].data_ptr(), n_spectra, first_unit,
+                                units_per_step, n_steps, d_recs[par].data_ptr(), side.cuda_stream)
+            out_free[par].record(side)
+            if xch is not None:
+                seq = xch.publish(d_recs[par].data_ptr(), side.cuda_stream)
+                if seq > 1:
+                    xch.merge(seq - 1, d_merged.data_ptr(), side.cuda_stream)   # the previous batch: its rows landed long ago
+                last_seq[0] = seq
+            elif world > 1:
+                S.gather_step_records(d_recs[par], world, out=d_gathers[par])   # NCCL all-gather, ~13 KB per rank
+                ctx.merge_step_records(d_gathers[par].data_ptr(), world, n_steps, d_merged.data_ptr(),
+                                       side.cuda_stream)
 
     def drain() -> None:
         """The last batch's exchange belongs to the timed region."""
-        if xch is not None:
-            if last_seq[0]:
-                xch.merge(last_seq[0], d_merged.data_ptr(), sh)
-        elif side is not None:
-            stream.wait_stream(side)
+        if xch is not None and last_seq[0]:
+            with torch.cuda.stream(side):
+                xch.merge(last_seq[0], d_merged.data_ptr(), side.cuda_stream)
+        stream.wait_stream(side)
 
     def barrier() -> None:
         if world > 1:
@@ -575,11 +590,14 @@ def main() -> None:
     if world > 1:
         if xch is not None and xch.status() != 0:
             raise SystemExit(f"bench.py: record exchange timed out waiting for a peer (sequence {xch.status()})")
-        local = d_recs[(step_no[0] - 1) & 1] if xch is None else d_rec
+        local = d_recs[(step_no[0] - 1) & 1]
         sums = local[:, :2].clone().to(torch.int64)
         ors = local[:, 2:].clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(ors, op=dist.ReduceOp.BOR)
+        ors_all = torch.empty((world,) + tuple(ors.shape), dtype=ors.dtype, device=dev)    # NCCL has no bitwise OR
+        dist.all_gather_into_tensor(ors_all.view(world * ors.shape[0], ors.shape[1]), ors.contiguous())
+        for r in range(world):
+            ors = ors | ors_all[r]
         hits_total = d_count.to(torch.int64).sum().reshape(1)
         dist.all_reduce(hits_total, op=dist.ReduceOp.SUM)
         ok_sum = bool(torch.equal(d_merged[:, :2].to(torch.int64), sums))

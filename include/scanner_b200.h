@@ -150,6 +150,12 @@ SCN_API int scn_process_host(scn_ctx* ctx, const void* raw, uint32_t n_spectra, 
  * the ticket's stream and returns immediately.  scn_collect blocks until that work is done
  * and copies the results out.  Tickets complete in submit order. */
 SCN_API int scn_submit(scn_ctx* ctx, const void* raw, uint32_t n_spectra, uint32_t* ticket);
+/* scn_submit for a batch that lies in several pieces: runs[r] points at run_buffers[r] consecutive raw buffers
+ * (sum == n_spectra * averaging, in batch order).  One H2D copy per run, straight from the caller's memory when it
+ * is pinned (SampleQueue's slab: the consumer then never copies a sample on the host); pageable runs are packed
+ * through the slot's pinned staging buffer. */
+SCN_API int scn_submit_gather(scn_ctx* ctx, const void* const* runs, const uint32_t* run_buffers, uint32_t n_runs,
+                              uint32_t n_spectra, uint32_t* ticket);
 SCN_API int scn_collect(scn_ctx* ctx, uint32_t ticket, float* spectra_db, uint32_t* hit_mask,
                         uint32_t* hit_count, scn_hit* hits, float* td_max_min);
 

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("scn_free_pinned", _I, [_VP]),
     ("scn_process_host", _I, [_VP, _VP, _U32, _VP, _VP, _VP, _VP, _VP]),
     ("scn_submit", _I, [_VP, _VP, _U32, C.POINTER(_U32)]),
+    ("scn_submit_gather", _I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _U32, _U32, C.POINTER(_U32)]),
     ("scn_collect", _I, [_VP, _U32, _VP, _VP, _VP, _VP, _VP]),
     ("scn_launch_device", _I, [_VP, _VP, _U32, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("scn_launch_count", _U64, [_VP]),
@@ -261,6 +262,13 @@ class SpectrumSense:
     def submit(self, raw_ptr: int, n_spectra: int) -> int:
         ticket = _U32(0)
         _check(self._lib.scn_submit(self._ctx, _VP(raw_ptr), n_spectra, C.byref(ticket)))
+        return int(ticket.value)
+
+    def submit_gather(self, run_ptrs: list[int], run_buffers: list[int], n_spectra: int) -> int:
+        ticket = _U32(0)
+        ptrs = (_VP * len(run_ptrs))(*run_ptrs)
+        cnts = (_U32 * len(run_buffers))(*run_buffers)
+        _check(self._lib.scn_submit_gather(self._ctx, ptrs, cnts, len(run_ptrs), n_spectra, C.byref(ticket)))
         return int(ticket.value)
 
     def collect(self, ticket: int, spectra=None, masks=None, counts=None, hits=None, tdmm=None) -> None:

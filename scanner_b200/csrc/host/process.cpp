@@ -74,8 +74,11 @@ void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t
     if (doWrite) {
       uint64_t end = sequenceId + m_postTrigger + 1, cur = m_endSequenceId;
       while (cur < end && !m_endSequenceId.compare_exchange_weak(cur, end)) {}
-    } else if (sequenceId == m_endSequenceId) {
-      m_sampleQueue->EndWrite(sequenceId);
+    } else if (sequenceId == m_endSequenceId || (m_averaging > 1 && sequenceId > m_endSequenceId)) {
+      // K == 1: the reference's strict equality (process.cpp:262).  With K-FFT averaging only the first id of every
+      // K-group arrives here (0, K, 2K, ...), so the end of the window may never be hit exactly: the first group
+      // at or past it closes the window AT the end id.
+      m_sampleQueue->EndWrite(m_endSequenceId);
       m_writing = false;
     }
   } else if (doWrite && !m_fileNameBase.empty()) {
@@ -105,8 +108,9 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   // stream), batch i+1 is drained from the queue and staged.  Results are never held back waiting for
   // more input: with nothing queued the in-flight batch is collected at once.
   struct InFlight {
-    void* staging = nullptr;                       // contiguous pinned batch
-    const void* src = nullptr;                     // what was submitted: staging, or the batch's own slab run
+    void* staging = nullptr;                       // contiguous pinned batch (only used when the slab runs are too short)
+    std::vector<const void*> runs;                 // what is submitted: address runs of the queue's pinned slab ...
+    std::vector<uint32_t> runBuffers;              // ... and their lengths in buffers (or the staging copy as one run)
     std::vector<SampleQueue::MessageType*> batch;
     uint32_t ticket = 0, nSpectra = 0;
     bool active = false;
@@ -118,20 +122,44 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
 
   const bool zeroCopy = m_zeroCopy && q->IsPinnedSlab();
-  // where the batch is submitted from: its own run of the pinned slab when it is one, else a copy in `staging`
+  // What a batch is submitted from.  The messages live in ONE pinned slab and the pool recycles first-in first-out,
+  // so a drained batch is a handful of address runs (one per producer append, or one in all with a single
+  // producer): those go to scn_submit_gather as they lie -- one H2D copy per run, no host copy of any sample.
+  // Only when the runs are short (single-buffer appends racing a LIFO pool, or no pinned slab) is the batch packed
+  // into `staging` first, as the reference's consumer copies every message (process.cpp:293-295).
+  std::vector<char> overflowRaw;
   auto stage = [&](InFlight& f) {
     const uint32_t count = f.nSpectra * K;
-    bool oneRun = zeroCopy && count > 0;
-    for (uint32_t i = 1; oneRun && i < count; i++)
-      oneRun = static_cast<char*>(f.batch[i]->GetData()) == static_cast<char*>(f.batch[i - 1]->GetData()) + bufBytes;
-    if (oneRun) {
-      f.src = f.batch[0]->GetData();
-      m_zeroCopyBatches++;
-      return;
+    f.runs.clear();
+    f.runBuffers.clear();
+    if (count == 0) return;
+    if (zeroCopy) {
+      for (uint32_t i = 0; i < count; i++) {
+        char* p = static_cast<char*>(f.batch[i]->GetData());
+        if (!f.runs.empty() && p == static_cast<const char*>(f.runs.back()) + size_t(f.runBuffers.back()) * bufBytes) {
+          f.runBuffers.back()++;
+        } else {
+          f.runs.push_back(p);
+          f.runBuffers.push_back(1);
+        }
+      }
+      if (f.runs.size() == 1 || size_t(count) >= 16 * f.runs.size()) {   // runs average >= 16 buffers: DMA them in place
+        m_zeroCopyBatches++;
+        return;
+      }
+      f.runs.clear();
+      f.runBuffers.clear();
     }
     for (uint32_t i = 0; i < count; i++)
       memcpy(static_cast<char*>(f.staging) + size_t(i) * bufBytes, f.batch[i]->GetData(), bufBytes);
-    f.src = f.staging;
+    f.runs.push_back(f.staging);
+    f.runBuffers.push_back(count);
+  };
+  auto submit = [&](InFlight& f) {
+    if (f.nSpectra == 0) return;
+    if (scn_submit_gather(ctx, f.runs.data(), f.runBuffers.data(), uint32_t(f.runs.size()), f.nSpectra, &f.ticket) != SCN_OK)
+      Die("scn_submit_gather");
+    m_launches++;
   };
   bool processedAny = false;
   uint64_t lastSequenceId = 0;
@@ -172,7 +200,10 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
               fullHits.resize(N);
             }
             uint32_t c2 = 0;
-            if (scn_process_host(fullCtx, static_cast<const char*>(f.src) + size_t(s) * K * bufBytes, 1, nullptr, nullptr,
+            overflowRaw.resize(size_t(K) * bufBytes);
+            for (uint32_t k = 0; k < K; k++)
+              memcpy(overflowRaw.data() + size_t(k) * bufBytes, f.batch[size_t(s) * K + k]->GetData(), bufBytes);
+            if (scn_process_host(fullCtx, overflowRaw.data(), 1, nullptr, nullptr,
                                  &c2, fullHits.data(), nullptr) != SCN_OK)
               Die("scn_process_host");
             list = fullHits.data();
@@ -207,29 +238,25 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   while (true) {
     InFlight& next = slot[cur];
     InFlight& prev = slot[cur ^ 1];
-    const uint32_t n = q->GetNextBatch(next.batch, maxSpectra * K, K, /*wait=*/!prev.active, zeroCopy);
+    const uint32_t n = q->GetNextBatch(next.batch, maxSpectra * K, K, /*wait=*/!prev.active, false,
+                                       m_minBatch, m_lingerMicros);
     if (n) {
       next.nSpectra = n / K;                              // a trailing partial group at end of stream is dropped
       stage(next);
-      if (next.nSpectra) {
-        if (scn_submit(ctx, next.src, next.nSpectra, &next.ticket) != SCN_OK) Die("scn_submit");
-        m_launches++;
-      }
+      submit(next);
       next.active = true;
     }
     if (prev.active) finish(prev);
     if (n) cur ^= 1;
     else if (!slot[0].active && !slot[1].active) {
       // nothing in flight and the non-blocking poll found nothing: block, or stop when drained
-      const uint32_t m = q->GetNextBatch(slot[cur].batch, maxSpectra * K, K, /*wait=*/true, zeroCopy);
+      const uint32_t m = q->GetNextBatch(slot[cur].batch, maxSpectra * K, K, /*wait=*/true, false,
+                                         m_minBatch, m_lingerMicros);
       if (m == 0) break;
       InFlight& f = slot[cur];
       f.nSpectra = m / K;
       stage(f);
-      if (f.nSpectra) {
-        if (scn_submit(ctx, f.src, f.nSpectra, &f.ticket) != SCN_OK) Die("scn_submit");
-        m_launches++;
-      }
+      submit(f);
       f.active = true;
       cur ^= 1;
     }

@@ -49,10 +49,14 @@ class ProcessSamples {
   void SetDevice(int device) { m_device = device; }
   void SetAveraging(uint32_t k) { m_averaging = k ? k : 1; }
   void SetMaxBatch(uint32_t maxBatch) { m_maxBatch = maxBatch ? maxBatch : 1; }
-  // Hand batches to scn_submit straight from the queue's pinned slab (no staging copy) whenever a drained batch is
-  // one contiguous address run; the queue then recycles its messages FIFO so that this is the common case.
-  // Off by default (not yet measured on a GPU; verified against the goldens through tests/mock_abi).
+  // Hand batches to the GPU straight from the queue's pinned slab (scn_submit_gather: one H2D copy per address run, no
+  // host copy) whenever a drained batch is made of long runs; the queue then recycles its messages FIFO so that this is
+  // the common case.  On by default; off == always pack the batch into a staging buffer first.
   void SetZeroCopy(bool on) { m_zeroCopy = on; }
+  // Batching policy.  Default (0, 0): take whatever is queued and launch at once -- results are never held back.
+  // (minBatch, micros): once something is queued, linger up to `micros` for `minBatch` buffers, so a fast source gets
+  // launches of thousands of buffers instead of dozens (per-launch CPU cost is what bounds a GPU consumer).
+  void SetBatchLinger(uint32_t minBatch, uint32_t micros) { m_minBatch = minBatch; m_lingerMicros = micros; }
   uint64_t GetZeroCopyBatches() const { return m_zeroCopyBatches; }
   void SetOutput(FILE* out) { m_out = out; }                               // nullptr silences printing
   void SetDetectionSink(std::function<void(const Detection&)> sink) { m_sink = std::move(sink); }
@@ -88,7 +92,8 @@ class ProcessSamples {
   std::atomic<uint64_t> m_buffersProcessed{0}, m_hitCount{0}, m_launches{0};
   std::atomic<bool> m_writing{false};
   std::atomic<uint64_t> m_endSequenceId{0};
-  bool m_zeroCopy = false;
+  bool m_zeroCopy = true;
+  uint32_t m_minBatch = 0, m_lingerMicros = 0;
   std::atomic<uint64_t> m_zeroCopyBatches{0};
   uint32_t m_fileCounter = 0;                      // process.cpp:169
   std::shared_ptr<scn_ctx> m_writeCtx;             // converts recorded messages (scn_convert_host), writer thread only;

@@ -1,6 +1,7 @@
 #include "sampleQueue.h"
 
 #include <cassert>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,9 +63,19 @@ SampleQueue::~SampleQueue() {
   }
 }
 
+// messageQueue.h:67-72: every buffer before the SECOND scan-start marker is dropped.  Caller holds m_allocMutex
+// (which also serialises several producers' view of the iteration count).
+bool SampleQueue::AcceptOrDrop(time_t time) {
+  if (time) m_iterationCount++;
+  if (m_dropFirstSweep && m_iterationCount < 2) {
+    m_dropped++;
+    return false;
+  }
+  return true;
+}
+
 SampleQueue::MessageType* SampleQueue::Allocate() {
-  std::unique_lock<std::mutex> cacheLock(m_allocMutex);          // uncontended with a single producer
-  if (m_allocCache.empty()) {
+  if (m_allocCache.empty()) {                                    // caller holds m_allocMutex
     std::unique_lock<std::mutex> lock(m_poolMutex);
     m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
     for (size_t i = 0; i < kAllocChunk && !m_free.empty(); i++) {
@@ -89,14 +100,82 @@ void SampleQueue::Free(MessageType* m) {
   m_poolAvailable.notify_one();
 }
 
+// `count` free messages, oldest first in FIFO mode so that they form as few address runs as possible.
+// Caller holds m_allocMutex.  Blocks while the pool is empty (the consumers return messages in batches).
+void SampleQueue::AllocateMany(uint32_t count, std::vector<MessageType*>& out) {
+  out.clear();
+  while (out.size() < count) {
+    while (!m_allocCache.empty() && out.size() < count) {
+      out.push_back(m_allocCache.front());
+      m_allocCache.pop_front();
+    }
+    if (out.size() == count) break;
+    std::unique_lock<std::mutex> lock(m_poolMutex);
+    m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
+    while (!m_free.empty() && out.size() < count) {
+      if (m_fifoPool) { out.push_back(m_free.front()); m_free.pop_front(); }
+      else { out.push_back(m_free.back()); m_free.pop_back(); }
+    }
+  }
+}
+
+void SampleQueue::AppendSamplesBatch(const void* interleavedSamples, uint32_t count, const double* centerFrequencies,
+                                     const time_t* times) {
+  assert(m_kind != Short);                    // the split layout has no batched form (two pointers per buffer)
+  const char* src = static_cast<const char*>(interleavedSamples);
+  // pieces small enough that neither the pool nor the queue bound can deadlock on one batch
+  const uint32_t piece = m_bufferCount / 4 ? m_bufferCount / 4 : 1;
+  std::vector<MessageType*> msgs;
+  std::vector<uint32_t> accepted;
+  for (uint32_t first = 0; first < count; first += piece) {
+    const uint32_t n = count - first < piece ? count - first : piece;
+    accepted.clear();
+    {
+      std::unique_lock<std::mutex> cacheLock(m_allocMutex);
+      for (uint32_t i = 0; i < n; i++)
+        if (AcceptOrDrop(times ? times[first + i] : 0)) accepted.push_back(first + i);
+      if (accepted.empty()) continue;
+      AllocateMany(uint32_t(accepted.size()), msgs);
+    }
+    // copy outside every lock: one memcpy per run that is contiguous in BOTH the source and the slab
+    for (size_t i = 0; i < accepted.size();) {
+      size_t j = i + 1;
+      while (j < accepted.size() && accepted[j] == accepted[j - 1] + 1 &&
+             static_cast<char*>(msgs[j]->m_data) == static_cast<char*>(msgs[j - 1]->m_data) + m_bufferBytes) j++;
+      memcpy(msgs[i]->m_data, src + size_t(accepted[i]) * m_bufferBytes, (j - i) * m_bufferBytes);
+      i = j;
+    }
+    for (size_t i = 0; i < accepted.size(); i++) {
+      MessageHeader& header = msgs[i]->m_header;
+      header.m_time = times ? times[accepted[i]] : 0;
+      header.m_frequency = centerFrequencies[accepted[i]];
+      header.m_kind = MessageHeader::ProcessData;
+      header.m_referenceCount = 0;
+    }
+    std::unique_lock<std::mutex> lock(m_mutex);
+    m_conditionFull.wait(lock, [&] { return m_buffer.size() + accepted.size() <= m_bufferCount || m_buffer.empty(); });
+    for (size_t i = 0; i < accepted.size(); i++) {
+      msgs[i]->m_header.m_sequenceId = m_nextBufferSequenceId++;
+      m_buffer.push_back(msgs[i]);
+    }
+    if (m_waiters && m_buffer.size() >= m_waitNeed) m_conditionEmpty.notify_all();
+    ClearAck();
+  }
+}
+
+void SampleQueue::SetProducerCount(uint32_t producers) {
+  std::unique_lock<std::mutex> lock(m_mutex);
+  m_producersLeft = producers ? producers : 1;
+}
+
 void SampleQueue::SynchronizedAppend(const void* a, size_t aBytes, const void* b, size_t bBytes,
                                      double centerFrequency, time_t time) {
-  if (time) m_iterationCount++;
-  if (m_dropFirstSweep && m_iterationCount < 2) {      // messageQueue.h:67-72
-    m_dropped++;
-    return;
+  MessageType* message;
+  {
+    std::unique_lock<std::mutex> cacheLock(m_allocMutex);          // uncontended with a single producer
+    if (!AcceptOrDrop(time)) return;
+    message = Allocate();
   }
-  MessageType* message = Allocate();
   memcpy(message->m_data, a, aBytes);
   if (bBytes) memcpy(static_cast<char*>(message->m_data) + aBytes, b, bBytes);
   MessageHeader& header = message->m_header;
@@ -162,13 +241,23 @@ void SampleQueue::SetFifoPool(bool fifo) {
 }
 
 uint32_t SampleQueue::GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple,
-                                   bool wait, bool contiguous) {
+                                   bool wait, bool contiguous, uint32_t minCount, uint32_t maxWaitMicros) {
   out.clear();
   if (multiple == 0) multiple = 1;
   std::unique_lock<std::mutex> lock(m_mutex);
   // a group of `multiple` buffers forms one averaged spectrum: wait for a whole group (or the end)
-  if (wait) WaitForQueued(lock, multiple);
-  else if (!(m_done || m_buffer.size() >= multiple)) return 0;
+  if (wait) {
+    WaitForQueued(lock, multiple);
+    if (minCount > maxCount) minCount = maxCount;
+    if (maxWaitMicros && !m_done && m_buffer.size() < minCount) {
+      // linger: a deeper batch is worth a bounded wait (the producer notifies when `minCount` are queued)
+      m_waiters++;
+      if (m_waitNeed == 0 || minCount < m_waitNeed) m_waitNeed = minCount;
+      m_conditionEmpty.wait_for(lock, std::chrono::microseconds(maxWaitMicros),
+                                [&] { return m_done || m_buffer.size() >= minCount; });
+      if (--m_waiters == 0) m_waitNeed = 0;
+    }
+  } else if (!(m_done || m_buffer.size() >= multiple)) return 0;
   size_t take = m_buffer.size() < maxCount ? m_buffer.size() : maxCount;
   if (contiguous) {
     size_t run = take ? 1 : 0;
@@ -302,6 +391,11 @@ void SampleQueue::WriteThreadWorker() {
 
 void SampleQueue::SetIsDone() {
   std::unique_lock<std::mutex> lock(m_mutex);
+  if (m_producersLeft > 1) {       // other producer threads are still appending
+    m_producersLeft--;
+    return;
+  }
+  m_producersLeft = 0;
   m_done = true;
   m_conditionEmpty.notify_all();
 }

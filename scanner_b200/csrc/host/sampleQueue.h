@@ -72,6 +72,16 @@ class SampleQueue {
   void AppendSamples(int16_t shortComplexSamples[][2], double centerFrequency, time_t time);
   void AppendSamples(int8_t (*byteComplexSamples)[2], double centerFrequency, time_t time);
   void AppendSamples(fftwf_complex* floatComplexSamples, double centerFrequency, time_t time);
+  // Batched form of the three interleaved overloads above -- `count` consecutive buffers of the queue's kind, e.g.
+  // one 262 144-byte HackRF transfer = 64 buffers of 2048 int8 IQ samples (hackRFSource.cpp:251-264).  Exactly
+  // `count` AppendSamples calls in order (drop rule, sequence ids, FIFO), but ONE pool transaction, one memcpy per
+  // contiguous slab run and one queue lock.  times == nullptr: all zero.  Safe to call from several producer
+  // threads (SetProducerCount); a batch's buffers get consecutive sequence ids.
+  void AppendSamplesBatch(const void* interleavedSamples, uint32_t count, const double* centerFrequencies,
+                          const time_t* times);
+  // Number of producer threads that will each call SetIsDone() when they finish (default 1, the reference's
+  // single source thread): the queue is done when the last one has.
+  void SetProducerCount(uint32_t producers);
 
   MessageType* GetNextSamples();                                   // nullptr == done and drained
   // Blocks for the first message, then takes what is queued: up to maxCount, a multiple of `multiple`
@@ -80,8 +90,12 @@ class SampleQueue {
   // finish an in-flight batch instead of sleeping on the queue).
   // contiguous == true: the batch stops where the next message does not follow the previous one in memory, so the
   // whole batch is ONE address run of the pinned slab and can be handed to scn_submit without a staging copy.
+  // minCount / maxWaitMicros (wait == true only): once a first group is queued, linger up to maxWaitMicros for at
+  // least minCount messages -- a GPU consumer wants launches of thousands of buffers, not of whatever happened to
+  // be queued when it looked; the linger bounds the latency this adds when the source is slow.
   uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1,
-                        bool wait = true, bool contiguous = false);
+                        bool wait = true, bool contiguous = false, uint32_t minCount = 0,
+                        uint32_t maxWaitMicros = 0);
   // Recycle messages first-in first-out (ascending slab addresses) instead of last-in first-out, so consecutive
   // appends land in consecutive slab slots.  Off by default; ProcessSamples::SetZeroCopy turns it on.
   void SetFifoPool(bool fifo);
@@ -115,6 +129,8 @@ class SampleQueue {
   void SynchronizedAppend(const void* a, size_t aBytes, const void* b, size_t bBytes,
                           double centerFrequency, time_t time);
   MessageType* Allocate();
+  void AllocateMany(uint32_t count, std::vector<MessageType*>& out);
+  bool AcceptOrDrop(time_t time);              // the drop rule of messageQueue.h:67-72; m_allocMutex held
   void Free(MessageType* m);
   void WaitForQueued(std::unique_lock<std::mutex>& lock, uint32_t need);   // m_mutex held
   uint32_t m_waiters = 0, m_waitNeed = 0;      // consumers asleep on m_conditionEmpty / the smallest count one waits for
@@ -130,6 +146,7 @@ class SampleQueue {
   uint64_t m_nextBufferSequenceId = 0;
   uint64_t m_dropped = 0;
   bool m_done = false;
+  uint32_t m_producersLeft = 1;
   std::atomic<bool> m_acknowledged{true};
   uint64_t m_writeStartSequenceId = 0, m_writeEndSequenceId = 0;
 

@@ -150,6 +150,19 @@ void ReplaySource::Append(SampleQueue* q, size_t b) {
 bool ReplaySource::GetNextSamples(SampleQueue* sampleQueue, double_t& centerFrequency) {
   if (m_next >= m_nBuffers || m_isDone) return false;
   centerFrequency = m_frequencies[m_next];
+  if (m_appendBatch > 1 && m_kind != SampleQueue::Short) {
+    const size_t n = m_nBuffers - m_next < m_appendBatch ? m_nBuffers - m_next : m_appendBatch;
+    const time_t* times = nullptr;
+    if (m_buffersPerSweep) {
+      m_times.assign(n, 0);
+      for (size_t i = 0; i < n; i++)
+        if ((m_next + i) % m_buffersPerSweep == 0) m_times[i] = time_t(1000000000 + m_next + i);
+      times = m_times.data();
+    }
+    sampleQueue->AppendSamplesBatch(m_raw + m_next * m_bufferBytes, uint32_t(n), m_frequencies + m_next, times);
+    m_next += n;
+    return true;
+  }
   Append(sampleQueue, m_next++);
   return true;
 }

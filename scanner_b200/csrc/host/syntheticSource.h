@@ -48,9 +48,15 @@ class ReplaySource : public SignalSource {
   bool StartStreaming(uint32_t numIterations, SampleQueue& sampleQueue) override;
   void ThreadWorker() override;
   double Retune(double frequency) override;
+  // Hand the queue `n` consecutive buffers per call (SampleQueue::AppendSamplesBatch) the way an SDR driver delivers
+  // a whole USB transfer at once (hackRFSource.cpp:251-264: 64 buffers per 262 144-byte transfer); 1 == one
+  // AppendSamples call per buffer.  Interleaved kinds only.
+  void SetAppendBatch(uint32_t n) { m_appendBatch = n ? n : 1; }
 
  private:
   void Append(SampleQueue* q, size_t b);
+  uint32_t m_appendBatch = 1;
+  std::vector<time_t> m_times;
   SampleQueue::SampleKind m_kind;
   const char* m_raw;
   const double* m_frequencies;

@@ -235,6 +235,7 @@ int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d
                      uint32_t* d_masks, uint32_t* d_counts, scn_hit* d_hits, cudaStream_t stream) {
   if (c->large) return launch_large(c, d_raw, n_spectra, d_spectra, d_masks, d_counts, d_hits, stream);
   scn::KernelParams p{};
+
   p.raw = static_cast<const uint8_t*>(d_raw);
   p.window = c->d_window;
   p.twiddles = c->d_twiddles;
@@ -473,17 +474,17 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     if (e == cudaSuccess) e = cudaMemcpy(c->d_window, w.data(), sizeof(float) * cf.sample_count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(SCN_ERR_CUDA, "window upload failed: %s", cudaGetErrorString(e)));
     std::vector<float2> tw = build_twiddles(c->log2n2);
-    if (c->variant.twiddle_layout == 2) {      // scn_p64.cuh: twA[(r-1)*64 + k] = W_4096^(k r); twB[c*128 + t] = W_8192^(t + 128 c)
-      tw.assign(63 * 64 + 32 * 128, make_float2(0.f, 0.f));
+    if (c->variant.twiddle_layout == 2) {      // scn_p64.cuh: twA[(r-1)*64 + k] = W_4096^(k r); twB[m*64 + kk] = W_8192^(kk + 64 m)
+      tw.assign(63 * 64 + 32 * 64, make_float2(0.f, 0.f));
       for (int r = 1; r < 64; r++)
         for (int k = 0; k < 64; k++) {
           const double a = -2.0 * kPi * double(k) * double(r) / 4096.0;
           tw[size_t(r - 1) * 64 + k] = make_float2(float(std::cos(a)), float(std::sin(a)));
         }
-      for (int cc = 0; cc < 32; cc++)
-        for (int t = 0; t < 128; t++) {
-          const double a = -2.0 * kPi * double(t + 128 * cc) / 8192.0;
-          tw[size_t(63 * 64) + size_t(cc) * 128 + t] = make_float2(float(std::cos(a)), float(std::sin(a)));
+      for (int m = 0; m < 32; m++)
+        for (int kk = 0; kk < 64; kk++) {
+          const double a = -2.0 * kPi * double(kk + 64 * m) / 8192.0;
+          tw[size_t(63 * 64) + size_t(m) * 64 + kk] = make_float2(float(std::cos(a)), float(std::sin(a)));
         }
     }
     if (c->variant.twiddle_layout == 1) {      // warp-per-transform kernel: exp(-2 pi i lane r / N), r = 1..63
@@ -591,26 +592,10 @@ SCN_API int scn_launch_device(scn_ctx* c, const void* d_raw, uint32_t n_spectra,
                           static_cast<cudaStream_t>(stream));
 }
 
-SCN_API int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t* ticket) {
-  if (!c || !ticket) return fail(SCN_ERR_INVALID, "ctx/ticket is NULL");
-  if (n_spectra == 0 || !raw) return fail(SCN_ERR_INVALID, "empty submit");
-  if (n_spectra > c->cfg.max_spectra)
-    return fail(SCN_ERR_CAPACITY, "n_spectra %u exceeds max_spectra %u", n_spectra, c->cfg.max_spectra);
-  SCN_CUDA(cudaSetDevice(c->cfg.device));
-  const uint32_t idx = c->next_slot;
-  Slot& s = c->slots[idx];
-  if (s.busy) return fail(SCN_ERR_BUSY, "ticket slot %u has not been collected", idx);
-  int rc = ensure_slot(c, s);
-  if (rc != SCN_OK) return rc;
-  const size_t bytes = size_t(n_spectra) * c->K * c->buf_bytes;
-  const void* src = raw;
-  if (!is_device_accessible_host(raw)) {
-    // pageable caller memory: stage through pinned memory so the copy is a real async DMA
-    if (!s.h_raw) SCN_CUDA(cudaMallocHost(&s.h_raw, size_t(c->cfg.max_spectra) * c->K * c->buf_bytes));
-    std::memcpy(s.h_raw, raw, bytes);
-    src = s.h_raw;
-  }
-  SCN_CUDA(cudaMemcpyAsync(s.d_raw, src, bytes, cudaMemcpyHostToDevice, s.stream));
+namespace {
+// kernel + D2H of the detection records + completion event on the slot's stream, after its raw bytes were enqueued
+int finish_submit(scn_ctx* c, Slot& s, uint32_t idx, uint32_t n_spectra, uint32_t* ticket) {
+  int rc;
   if (c->time_domain) {
     rc = launch_time_domain(c, s.d_raw, n_spectra, s.d_counts, s.d_td, s.stream);
     if (rc != SCN_OK) return rc;
@@ -632,6 +617,73 @@ SCN_API int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t
   *ticket = idx;
   c->next_slot = (idx + 1) % uint32_t(c->slots.size());
   return SCN_OK;
+}
+}  // namespace
+
+SCN_API int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t* ticket) {
+  if (!c || !ticket) return fail(SCN_ERR_INVALID, "ctx/ticket is NULL");
+  if (n_spectra == 0 || !raw) return fail(SCN_ERR_INVALID, "empty submit");
+  if (n_spectra > c->cfg.max_spectra)
+    return fail(SCN_ERR_CAPACITY, "n_spectra %u exceeds max_spectra %u", n_spectra, c->cfg.max_spectra);
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  const uint32_t idx = c->next_slot;
+  Slot& s = c->slots[idx];
+  if (s.busy) return fail(SCN_ERR_BUSY, "ticket slot %u has not been collected", idx);
+  int rc = ensure_slot(c, s);
+  if (rc != SCN_OK) return rc;
+  const size_t bytes = size_t(n_spectra) * c->K * c->buf_bytes;
+  const void* src = raw;
+  if (!is_device_accessible_host(raw)) {
+    // pageable caller memory: stage through pinned memory so the copy is a real async DMA
+    if (!s.h_raw) SCN_CUDA(cudaMallocHost(&s.h_raw, size_t(c->cfg.max_spectra) * c->K * c->buf_bytes));
+    std::memcpy(s.h_raw, raw, bytes);
+    src = s.h_raw;
+  }
+  SCN_CUDA(cudaMemcpyAsync(s.d_raw, src, bytes, cudaMemcpyHostToDevice, s.stream));
+  return finish_submit(c, s, idx, n_spectra, ticket);
+}
+
+SCN_API int scn_submit_gather(scn_ctx* c, const void* const* runs, const uint32_t* run_buffers, uint32_t n_runs,
+                              uint32_t n_spectra, uint32_t* ticket) {
+  if (!c || !ticket || !runs || !run_buffers) return fail(SCN_ERR_INVALID, "submit_gather: NULL argument");
+  if (n_spectra == 0 || n_runs == 0) return fail(SCN_ERR_INVALID, "empty submit");
+  if (n_spectra > c->cfg.max_spectra)
+    return fail(SCN_ERR_CAPACITY, "n_spectra %u exceeds max_spectra %u", n_spectra, c->cfg.max_spectra);
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n_runs; r++) {
+    if (!runs[r] || run_buffers[r] == 0) return fail(SCN_ERR_INVALID, "submit_gather: run %u is empty", r);
+    total += run_buffers[r];
+  }
+  if (total != uint64_t(n_spectra) * c->K)
+    return fail(SCN_ERR_INVALID, "submit_gather: runs hold %llu buffers, n_spectra * averaging is %llu",
+                (unsigned long long)total, (unsigned long long)(uint64_t(n_spectra) * c->K));
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  const uint32_t idx = c->next_slot;
+  Slot& s = c->slots[idx];
+  if (s.busy) return fail(SCN_ERR_BUSY, "ticket slot %u has not been collected", idx);
+  int rc = ensure_slot(c, s);
+  if (rc != SCN_OK) return rc;
+  // one H2D copy per run, back to back on the slot's stream, into consecutive device addresses; pageable runs
+  // are packed into the slot's pinned staging buffer first (then it is ONE copy)
+  bool pinned = true;
+  for (uint32_t r = 0; r < n_runs && pinned; r++) pinned = is_device_accessible_host(runs[r]);
+  size_t off = 0;
+  if (!pinned) {
+    if (!s.h_raw) SCN_CUDA(cudaMallocHost(&s.h_raw, size_t(c->cfg.max_spectra) * c->K * c->buf_bytes));
+    for (uint32_t r = 0; r < n_runs; r++) {
+      const size_t bytes = size_t(run_buffers[r]) * c->buf_bytes;
+      std::memcpy(static_cast<char*>(s.h_raw) + off, runs[r], bytes);
+      off += bytes;
+    }
+    SCN_CUDA(cudaMemcpyAsync(s.d_raw, s.h_raw, off, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    for (uint32_t r = 0; r < n_runs; r++) {
+      const size_t bytes = size_t(run_buffers[r]) * c->buf_bytes;
+      SCN_CUDA(cudaMemcpyAsync(static_cast<char*>(s.d_raw) + off, runs[r], bytes, cudaMemcpyHostToDevice, s.stream));
+      off += bytes;
+    }
+  }
+  return finish_submit(c, s, idx, n_spectra, ticket);
 }
 
 SCN_API int scn_collect(scn_ctx* c, uint32_t ticket, float* spectra_db, uint32_t* hit_mask,

@@ -4,9 +4,11 @@
 //
 // T = N/64 threads own one transform (2 or 4 warps per CTA):
 //   N = 4096 = 64 x 64    : radix-64 on column t, ONE exchange, radix-64 with twiddles W_4096^(t r)
-//   N = 8192 = 64 x 64 x 2: the same two passes (twiddles W_4096^((t mod 64) r)), a second exchange, then
-//                           32 radix-2 butterflies with twiddles W_8192^(t + 128 c)
-// In both cases the outputs are bins t + T q: coalesced stores.  Against the 16-points-per-thread plans
+//   N = 8192 = 64 x 64 x 2: the same two passes (twiddles W_4096^((t mod 64) r)); threads t and t ^ 64 then hold the
+//                           even- / odd-column halves Z_0, Z_1 of the same 128-point row, so the last radix-2 is a
+//                           PAIRWISE swap of 32 points each through 32 KB of the tile, then 32 butterflies
+//                           Z_0[k] +- W_8192^(kk + 64 k) Z_1[k] per thread
+// In both cases a warp's lanes hold 32 consecutive bins in every register slot: coalesced stores, warp-owned mask words.  Against the 16-points-per-thread plans
 // ([16,16,16] / [2,16,16,16]) this saves one exchange, keeps CTAs small (several independent CTAs per SM
 // drift apart, so one CTA's exchange overlaps another's butterflies) and runs the radix-64 stages on
 // packed fp32x2 math with W64 twiddles as immediates (scn_wpt.cuh).
@@ -45,12 +47,12 @@ constexpr size_t p64_smem_bytes() {
                                         : G::kStageOffset + size_t(G::N) * KindTraits<KIND>::kBytes;
 }
 // twiddle tables (host: scn_api.cu, layout 2): twA[(r-1)*64 + k] = exp(-2 pi i k r / 4096), r = 1..63, k < 64;
-//                                             twB[c*128 + t]    = exp(-2 pi i (t + 128 c) / 8192), c < 32, t < 128
-// (the kernel reads rows c < 16 only: row c + 16 is row c times -i, applied for free in the butterfly -- with the
-//  mirrored window taps this brings the per-CTA table working set from 78 KB to 39 KB, inside the 64 KB of L1
-//  that two 66 KB CTAs leave; ncu had the tables hitting L1 only 34 % of the time)
+//                                             twB[m*64 + kk]    = exp(-2 pi i (kk + 64 m) / 8192), m < 32, kk < 64
+// (threads t >= 64 need W^(kk + 64 (m + 32)) = the same entry times -i, applied for free in the butterfly -- with the
+//  mirrored window taps the per-CTA table working set is 39 KB instead of 78 KB, inside the L1 that two 66 KB CTAs
+//  leave; ncu had the tables hitting L1 only 34 % of the time before)
 constexpr int kP64TwAElems = 63 * 64;
-constexpr int kP64TwBElems = 32 * 128;
+constexpr int kP64TwBElems = 32 * 64;
 
 #ifndef SCN_P64_MINCTAS
 #define SCN_P64_MINCTAS 2
@@ -99,10 +101,16 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     const uint32_t i = j ^ half;
     return !(j < p.dc_ignore || (N - j) < p.dc_ignore) && !(i < (half - p.use_window) || i > (half + p.use_window));
   };
-  // slot x of v[] after the last pass <-> output index q (FFT bin t + T q)
-  auto slot_q = [](int x) -> int { return LOG2N == 13 ? x : dft64_out_index(x); };
-  // mask word of (this warp, output q): ((32 warp + T q) ^ N/2) >> 5
-  auto word_of = [&](int q) -> uint32_t { return uint32_t(warp + (T / 32) * q) ^ uint32_t(N / 64); };
+  // FFT bin held in slot x of v[] after the last pass.  N = 4096: t + 64 q(x).  N = 8192 (row kk = t mod 64,
+  // column parity hi = t / 64): slots 0..31 hold X[kk + 64 (m + 32 hi)], slots 32..63 the same + 4096.
+  // Either way the lanes of a warp hold 32 CONSECUTIVE bins in a slot, i.e. exactly one mask word.
+  const uint32_t bin_base = LOG2N == 13 ? uint32_t(t & 63) + 2048u * uint32_t(t >> 6) : uint32_t(t);
+  auto bin_of = [&](int x) -> uint32_t {
+    return LOG2N == 13 ? bin_base + 64u * uint32_t(x & 31) + 4096u * uint32_t(x >> 5)
+                       : bin_base + uint32_t(T) * uint32_t(dft64_out_index(x));
+  };
+  // mask word (shifted index >> 5) of slot x for this warp
+  auto word_of = [&](int x) -> uint32_t { return ((bin_of(x) - uint32_t(lane)) ^ half) >> 5; };
 
   // int32 sums of I and Q over the staged buffer (utility.cpp:44-48): this thread's words t + T i
   auto staged_sums = [&](int& si, int& sq) {
@@ -166,22 +174,24 @@ spectrum_sense_p64_kernel(const KernelParams p) {
 #define SCN_P64_LAND 1
 #endif
   constexpr bool kLand = SCN_P64_LAND && !kStaged;
+  // N = 8192 lands in two halves (two arrivals per mbarrier phase): samples 4096.. as soon as the last full-tile
+  // gather is done -- the pairwise swap of the last radix-2 only needs the first 32 KB of the tile -- and samples
+  // 0..4095 after the swap, under the epilogue.
+  constexpr uint32_t kLandParts = (LOG2N == 13) ? 2u : 1u;
+  constexpr uint32_t kPartBytes = kRawBytes / kLandParts;
+  auto land_part = [&](size_t buffer, uint32_t part) {       // one thread; the tile region is no longer read
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, kPartBytes);
+    bulk_g2s(reinterpret_cast<unsigned char*>(tile) + size_t(part) * kPartBytes,
+             p.raw + buffer * kRawBytes + size_t(part) * kPartBytes, kPartBytes, bar);
+  };
   if constexpr (kLand) {
     if (t == 0) {
-      mbar_init(bar, 1);
-      mbar_expect_tx(bar, kRawBytes);
-      bulk_g2s(tile, p.raw + size_t(s) * K * kRawBytes, kRawBytes, bar);
+      mbar_init(bar, kLandParts);
+      for (uint32_t part = 0; part < kLandParts; part++) land_part(size_t(s) * K, part);
     }
     __syncthreads();
   }
-  auto land_next = [&](bool has_next, uint32_t ns, uint32_t nk) {
-    // every thread has passed a barrier after its last read of the tile
-    if (has_next && t == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, kRawBytes);
-      bulk_g2s(tile, p.raw + (size_t(ns) * K + nk) * kRawBytes, kRawBytes, bar);
-    }
-  };
   constexpr bool kPrefetch = SCN_P64_PREFETCH && !kStaged && !AVG && !kLand;
 #ifndef SCN_P64_PREFETCH_13
 #define SCN_P64_PREFETCH_13 16
@@ -274,7 +284,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     }
     if constexpr (kLand && LOG2N == 12) {
       __syncthreads();                                 // last gather done: the tile is free for the next raw buffer
-      land_next(has_next, ns, nk);
+      if (has_next && t == 0) land_part(size_t(ns) * K + nk, 0);
     }
     const int kk = t & 63;
     {
@@ -292,30 +302,53 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     }
     dft64_inplace(v);
     if constexpr (LOG2N == 13) {
+      // ---- pass 2: the 128-point row kk = (64-point DFT of its even columns, thread kk) + (odd columns, thread
+      // kk + 64): X[kk + 64 k] = Z_0[k] + W_8192^(kk + 64 k) Z_1[k], X[.. + 4096] = Z_0[k] - (same), k < 64.
+      // Thread kk takes k < 32, thread kk + 64 takes k >= 32: each sends the partner the 32 points it needs
+      // through the first 32 KB of the tile, layout [m][thread] (conflict-free both ways). ------------------------
+      const uint32_t hi = uint32_t(t) >> 6;            // warp-uniform
       __syncthreads();                                 // every thread has finished its gather of exchange 1
+      if constexpr (kLand) {
+        if (has_next && t == 0) land_part(size_t(ns) * K + nk, 1);   // upper 32 KB of the tile is free from here on
+      }
       {
-        const int j0 = ((t - kk) << 6) + kk;
-        float2* base = tile + j0 + (j0 >> 6);
+        float2* dst = tile + (t ^ 64);
+        if (hi == 0) {
 #pragma unroll
-        for (int x = 0; x < 64; x++) base[65 * dft64_out_index(x)] = v[x];
+          for (int x = 0; x < 64; x++) if (dft64_out_index(x) >= 32) dst[T * (dft64_out_index(x) - 32)] = v[x];   // Z_0[32 + m]
+        } else {
+#pragma unroll
+          for (int x = 0; x < 64; x++) if (dft64_out_index(x) < 32) dst[T * dft64_out_index(x)] = v[x];           // Z_1[m]
+        }
       }
       __syncthreads();
-      // ---- pass 2: 32 radix-2 butterflies j = t + 128 c: inputs j and j + 4096, twiddle W_8192^j ----------------
-      const float2* base = tile + t + (t >> 6);
+      {
+        const float2* src = tile + t;
+        const float2* tw = twB + kk;                   // W_8192^(kk + 64 m); threads t >= 64 need it times -i
+        float2 o[64];
+        if (hi == 0) {
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
-        const float2 w = __ldg(twB + c * T + t);       // W_8192^(t + 128 c); row c + 16 is this times -i
-        const float2 a0 = base[GSTRIDE * c], a1 = base[GSTRIDE * (c + 16)];
-        const float2 b0 = cmul(base[GSTRIDE * c + 4096 + 64], w);
-        const float2 b1 = cmul(base[GSTRIDE * (c + 16) + 4096 + 64], w);
-        v[c] = cadd(a0, b0);                           // bin t + 128 c
-        v[32 + c] = csub(a0, b0);                      // bin t + 128 (c + 32)
-        v[16 + c] = add_mi(a1, b1);                    // bin t + 128 (c + 16)
-        v[48 + c] = sub_mi(a1, b1);                    // bin t + 128 (c + 48)
+          for (int m = 0; m < 32; m++) {
+            const float2 e = v[8 * (m & 7) + (m >> 3)];                  // own Z_0[m]
+            const float2 b = cmul(src[T * m], __ldg(tw + 64 * m));       // W Z_1[m]
+            o[m] = cadd(e, b);
+            o[32 + m] = csub(e, b);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 32; m++) {
+            const float2 b = cmul(v[8 * (m & 7) + (m >> 3) + 4], __ldg(tw + 64 * m));   // own Z_1[32 + m] times W^(kk + 64 m)
+            const float2 e = src[T * m];                                  // Z_0[32 + m]
+            o[m] = add_mi(e, b);                                          // ... times -i = W^(kk + 64 (m + 32))
+            o[32 + m] = sub_mi(e, b);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 64; x++) v[x] = o[x];
       }
       if constexpr (kLand) {
-        __syncthreads();                               // last read of the tile done: land the next raw buffer in it
-        land_next(has_next, ns, nk);
+        __syncthreads();                               // swap region read: the lower 32 KB may land now
+        if (has_next && t == 0) land_part(size_t(ns) * K + nk, 0);
       }
     }
 
@@ -351,19 +384,19 @@ spectrum_sense_p64_kernel(const KernelParams p) {
         if (has_next) { finish_dc(sred + 2 * G::WARPS * tpar, dci, dcq); tpar ^= 1u; }
       }
     } else {
-      // ---- dB, spectrum out, detection (slot x <-> FFT bin t + T slot_q(x)) ----------------------------------------
+      // ---- dB, spectrum out, detection (slot x <-> FFT bin bin_of(x)) ----------------------------------------------
       uint32_t* sm = smask + spar * G::WORDS;
-      float* out = p.spectra ? p.spectra + size_t(s) * N + t : nullptr;
+      float* out = p.spectra ? p.spectra + size_t(s) * N : nullptr;
       bool anyraw = false;
 #pragma unroll
       for (int x = 0; x < 64; x++) {
         const float pbar = AVG ? __fmul_rn(v[x].x, p.inv_averaging) : v[x].x;
         const float db = kDbPerLog2 * __log2f(pbar);
         v[x].x = db;
-        if (out) out[T * slot_q(x)] = db;
+        if (out) out[bin_of(x)] = db;
         anyraw = anyraw || (db > p.threshold);          // strict >, NaN never hits (process.cpp:54)
       }
-      // this warp owns mask words word_of(q), q = 0..63: zero them (two per lane), then fill on demand
+      // this warp owns mask words word_of(x), x = 0..63: zero them (two per lane), then fill on demand
       sm[word_of(lane)] = 0u;
       sm[word_of(lane + 32)] = 0u;
       uint32_t hb_lo = 0, hb_hi = 0;                   // hit bits by slot x
@@ -376,11 +409,11 @@ spectrum_sense_p64_kernel(const KernelParams p) {
         // candidate test only for the (few) raw hits of this lane
         for (uint32_t rest = hb_lo; rest; rest &= rest - 1) {
           const int x = __ffs(rest) - 1;
-          if (!is_candidate(uint32_t(t) + T * slot_q(x))) hb_lo &= ~(1u << x);
+          if (!is_candidate(bin_of(x))) hb_lo &= ~(1u << x);
         }
         for (uint32_t rest = hb_hi; rest; rest &= rest - 1) {
           const int x = __ffs(rest) - 1;
-          if (!is_candidate(uint32_t(t) + T * slot_q(x + 32))) hb_hi &= ~(1u << x);
+          if (!is_candidate(bin_of(x + 32))) hb_hi &= ~(1u << x);
         }
         __syncwarp();
         uint32_t rem_lo = __reduce_or_sync(0xffffffffu, hb_lo), rem_hi = __reduce_or_sync(0xffffffffu, hb_hi);
@@ -389,7 +422,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
           if (rem_lo) { x = __ffs(rem_lo) - 1; rem_lo &= rem_lo - 1; } else { x = 32 + __ffs(rem_hi) - 1; rem_hi &= rem_hi - 1; }
           const uint32_t mine = (x < 32) ? (hb_lo >> x) & 1u : (hb_hi >> (x - 32)) & 1u;
           const uint32_t b = __ballot_sync(0xffffffffu, mine);
-          if (lane == 0) sm[word_of(slot_q(x))] = b;
+          if (lane == 0) sm[word_of(x)] = b;
         }
       }
       if constexpr (kDC) {
@@ -424,7 +457,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
         for (int x = 0; x < 64; x++) {
           const bool any_x = (x < 32) ? ((any_lo >> x) & 1u) : ((any_hi >> (x - 32)) & 1u);
           if (any_x) {                                 // warp-uniform, rare
-            const uint32_t word = word_of(slot_q(x));
+            const uint32_t word = word_of(x);
             uint32_t before = 0;
             for (uint32_t y = lane; y < word; y += 32) before += __popc(sm[y]);
             before = __reduce_add_sync(0xffffffffu, before);
@@ -434,7 +467,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
               const uint32_t rank = before + __popc(b & ((1u << lane) - 1u));
               if (rank < p.hit_cap) {
                 scn_hit h;
-                h.bin = (uint32_t(t) + T * slot_q(x)) ^ half;
+                h.bin = bin_of(x) ^ half;
                 h.power_db = v[x].x;
                 p.hits[size_t(s) * p.hit_cap + rank] = h;
               }

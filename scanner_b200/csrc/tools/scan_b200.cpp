@@ -9,7 +9,7 @@
 //                   <iterations> <seed> [threads] [averaging]
 //       seeded SyntheticSource sweep (first sweep dropped like the reference: needs iterations >= 2).
 //   scan_b200 record <kind> <N> <fs> <enob> <dc> <threshold> <win_type> <buffers_per_sweep> <raw_file> <freq_file>
-//                    <file_base> <pre_trigger> <post_trigger> [threads]
+//                    <file_base> <pre_trigger> <post_trigger> [threads] [averaging]
 //       same arguments as oracle/_ref/ref_tool record: triggered recording on (SampleQueue doWrite, ProcessSamples
 //       fileNameBase / preTrigger / postTrigger); file-name stamps 1500000000 + 1000 k like ref_tool's clock.
 //   scan_b200 hackrf <N> <fs> <start> <stop> <threshold> <iterations> <valid_length> <stream_file> [threads]
@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -99,11 +100,12 @@ int main(int argc, char** argv) {
     const double* freqs = reinterpret_cast<const double*>(fr.data());
     if (legacy) return RunLegacy(kind, n, fs, enob, dc, thr, win, raw, freqs, nbuf);
     ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs, nbuf, perSweep, fs, n);
+    if (getenv("SCN_APPEND_BATCH")) source.SetAppendBatch(atoi(getenv("SCN_APPEND_BATCH")));   // AppendSamplesBatch path
     ProcessSamples process(n, fs, enob, thr, win, ProcessSamples::Mode(mode), threads);
     SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
     source.Start();
     source.StartStreaming(1, queue);
-    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+    if (getenv("SCN_STAGING_COPY")) process.SetZeroCopy(false);
     process.StartProcessing(queue);
     source.Join();
     fflush(stdout);
@@ -121,18 +123,21 @@ int main(int argc, char** argv) {
     const std::string base = argv[12];
     const uint32_t pre = atoi(argv[13]), post = atoi(argv[14]);
     const uint32_t threads = argc > 15 ? atoi(argv[15]) : 1;
+    const uint32_t averaging = argc > 16 ? atoi(argv[16]) : 1;
     const size_t bb = SyntheticSource::BufferBytes(SampleQueue::SampleKind(kind), n);
     const size_t nbuf = raw.size() / bb;
     const double* freqs = reinterpret_cast<const double*>(fr.data());
     ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs, nbuf, perSweep, fs, n);
+    if (getenv("SCN_APPEND_BATCH")) source.SetAppendBatch(atoi(getenv("SCN_APPEND_BATCH")));
     ProcessSamples process(n, fs, enob, thr, win, ProcessSamples::FrequencyDomain, threads, base, 0.75, 0.0, pre, post);
+    process.SetAveraging(averaging);
     uint64_t stamps = 0;
     process.SetClock([&stamps]() { return time_t(1500000000 + 1000 * stamps++); });
     {
       SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, true);
       source.Start();
       source.StartStreaming(1, queue);
-      if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+      if (getenv("SCN_STAGING_COPY")) process.SetZeroCopy(false);
     process.StartProcessing(queue);
       source.Join();
     }                                                           // ~SampleQueue flushes and joins the writer
@@ -153,7 +158,7 @@ int main(int argc, char** argv) {
     ProcessSamples process(n, fs, 8, thr, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
     SampleQueue queue(SampleQueue::ByteComplex, 8, n, 1024, true, false);
     source.StartStreaming(iterations, queue);
-    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+    if (getenv("SCN_STAGING_COPY")) process.SetZeroCopy(false);
     process.StartProcessing(queue);
     source.Join();
     fflush(stdout);
@@ -176,7 +181,7 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     source.Start();
     source.StartStreaming(iterations, queue);
-    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+    if (getenv("SCN_STAGING_COPY")) process.SetZeroCopy(false);
     process.StartProcessing(queue);
     source.Join();
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -187,15 +192,20 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (cmd == "bench" && argc >= 8) {
-    // scan_b200 bench <kind> <N> <enob> <dc> <distinct_buffers> <total_buffers> [threads] [max_batch]
-    // Throughput of the plugin surface itself: a ReplaySource cycling over `distinct` synthetic buffers pushes
-    // `total` raw buffers through SampleQueue into GPU ProcessSamples workers (printing off).
+    // scan_b200 bench <kind> <N> <enob> <dc> <distinct_buffers> <total_buffers> [threads] [max_batch] [producers]
+    //                 [append_batch] [linger_us]
+    // Throughput of the plugin surface itself: `producers` ReplaySource threads (think: one per SDR / USB transfer
+    // thread) push `total` raw buffers, `append_batch` per AppendSamplesBatch call (1 == the reference's one
+    // AppendSamples per buffer), through ONE SampleQueue into GPU ProcessSamples workers (printing off).
     const int kind = atoi(argv[2]);
     const uint32_t n = atoi(argv[3]), enob = atoi(argv[4]);
     const bool dc = atoi(argv[5]) != 0;
     const size_t distinct = strtoull(argv[6], nullptr, 0), total = strtoull(argv[7], nullptr, 0);
     const uint32_t threads = argc > 8 ? atoi(argv[8]) : 2;
     const uint32_t maxBatch = argc > 9 ? atoi(argv[9]) : 4096;
+    const uint32_t producers = argc > 10 && atoi(argv[10]) > 0 ? atoi(argv[10]) : 1;
+    const uint32_t appendBatch = argc > 11 && atoi(argv[11]) > 0 ? atoi(argv[11]) : 1;
+    const uint32_t lingerUs = argc > 12 ? atoi(argv[12]) : 0;
     const uint32_t fs = 20000000;
     const size_t bb = SyntheticSource::BufferBytes(SampleQueue::SampleKind(kind), n);
     std::vector<char> pool(distinct * bb);
@@ -209,23 +219,35 @@ int main(int argc, char** argv) {
       memcpy(raw.data() + b * bb, pool.data() + (b % distinct) * bb, bb);
       freqs[b] = 2.4075e9 + 15e6 * double(b % 50);
     }
-    ReplaySource source(SampleQueue::SampleKind(kind), raw.data(), freqs.data(), total, 0, fs, n);
+    std::vector<std::unique_ptr<ReplaySource>> sources;
+    for (uint32_t pr = 0; pr < producers; pr++) {
+      const size_t b0 = total * pr / producers, b1 = total * (pr + 1) / producers;
+      sources.emplace_back(new ReplaySource(SampleQueue::SampleKind(kind), raw.data() + b0 * bb, freqs.data() + b0,
+                                            b1 - b0, 0, fs, n));
+      sources.back()->SetAppendBatch(appendBatch);
+    }
     ProcessSamples process(n, fs, enob, 25.0f, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
     process.SetOutput(nullptr);
     process.SetMaxBatch(maxBatch);
+    if (lingerUs) process.SetBatchLinger(maxBatch / 2, lingerUs);
+    if (getenv("SCN_STAGING_COPY")) process.SetZeroCopy(false);
     SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 4 * maxBatch, dc, false);
     queue.SetDropFirstSweep(false);
+    queue.SetProducerCount(producers);
     const auto t0 = std::chrono::steady_clock::now();
-    source.Start();
-    source.StartStreaming(1, queue);
-    if (getenv("SCN_ZERO_COPY")) process.SetZeroCopy(true);
+    for (auto& src : sources) {
+      src->Start();
+      src->StartStreaming(1, queue);
+    }
     process.StartProcessing(queue);
-    source.Join();
+    for (auto& src : sources) src->Join();
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("plugin-surface throughput: %.1f Msamples/s (%zu buffers of %u samples, kind %d, %u worker threads, "
-           "batch <= %u, %lu hits, %lu launches of which %lu zero-copy, %.3f s)\n",
-           double(total) * n / sec / 1e6, total, n, kind, threads, maxBatch, (unsigned long)process.GetHitCount(),
-           (unsigned long)process.GetLaunchCount(), (unsigned long)process.GetZeroCopyBatches(), sec);
+    printf("plugin-surface throughput: %.1f Msamples/s (%zu buffers of %u samples, kind %d, %u producer threads x %u "
+           "buffers per append, %u worker threads, batch <= %u, linger %u us, %lu hits, %lu launches of which %lu "
+           "straight from the pinned slab, %.3f s)\n",
+           double(total) * n / sec / 1e6, total, n, kind, producers, appendBatch, threads, maxBatch, lingerUs,
+           (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount(),
+           (unsigned long)process.GetZeroCopyBatches(), sec);
     return 0;
   }
   fprintf(stderr, "scan_b200: bad arguments\n");

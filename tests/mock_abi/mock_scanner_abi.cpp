@@ -43,6 +43,11 @@ int fail(int code, const char* fmt, ...) {
 struct Result {
   bool busy = false;
   uint32_t n = 0;
+  // The real library reads the caller's (pinned) buffers ASYNCHRONOUSLY, some time between submit and collect.
+  // The mock models the worst case: it remembers only the POINTERS at submit and computes at collect, so a host
+  // that recycles a slab message before its ticket is collected reads recycled bytes here and fails the goldens.
+  std::vector<const void*> runs;
+  std::vector<uint32_t> run_buffers;
   std::vector<float> spectra, tdmm;
   std::vector<uint32_t> masks, counts;
   std::vector<scn_hit> hits;
@@ -108,13 +113,20 @@ uint32_t scn_mask_words(const scn_ctx* c) { return c ? c->words : 0; }
 int scn_alloc_pinned(size_t bytes, void** out) { *out = malloc(bytes ? bytes : 1); return *out ? SCN_OK : SCN_ERR_CUDA; }
 int scn_free_pinned(void* p) { free(p); return SCN_OK; }
 
-int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t* ticket) {
-  if (!c || !raw || !ticket) return fail(SCN_ERR_INVALID, "submit: bad arguments");
+int scn_submit_gather(scn_ctx* c, const void* const* runs, const uint32_t* run_buffers, uint32_t n_runs,
+                      uint32_t n_spectra, uint32_t* ticket) {
+  if (!c || !runs || !run_buffers || !ticket || n_runs == 0) return fail(SCN_ERR_INVALID, "submit: bad arguments");
   if (n_spectra > c->cfg.max_spectra) return fail(SCN_ERR_CAPACITY, "submit: %u > max_spectra %u", n_spectra, c->cfg.max_spectra);
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n_runs; r++) total += run_buffers[r];
+  if (total != uint64_t(n_spectra) * c->K) return fail(SCN_ERR_INVALID, "submit_gather: run lengths do not add up");
   for (uint32_t s = 0; s < c->slots.size(); s++)
     if (!c->slots[s].busy) {
-      compute(c, raw, n_spectra, c->slots[s]);
-      c->slots[s].busy = true;
+      Result& r = c->slots[s];
+      r.runs.assign(runs, runs + n_runs);
+      r.run_buffers.assign(run_buffers, run_buffers + n_runs);
+      r.n = n_spectra;
+      r.busy = true;
       c->launches++;
       *ticket = s;
       return SCN_OK;
@@ -122,10 +134,25 @@ int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t* ticket
   return fail(SCN_ERR_BUSY, "submit: no free ticket slot");
 }
 
+int scn_submit(scn_ctx* c, const void* raw, uint32_t n_spectra, uint32_t* ticket) {
+  if (!c || !raw) return fail(SCN_ERR_INVALID, "submit: bad arguments");
+  const uint32_t buffers = n_spectra * c->K;
+  return scn_submit_gather(c, &raw, &buffers, 1, n_spectra, ticket);
+}
+
 int scn_collect(scn_ctx* c, uint32_t ticket, float* spectra_db, uint32_t* hit_mask, uint32_t* hit_count, scn_hit* hits,
                 float* td_max_min) {
   if (!c || ticket >= c->slots.size() || !c->slots[ticket].busy) return fail(SCN_ERR_INVALID, "collect: bad ticket");
   Result& r = c->slots[ticket];
+  {                                           // "the DMA and the kernel happen now"
+    std::vector<char> staged(size_t(r.n) * c->K * c->buf_bytes);
+    size_t off = 0;
+    for (size_t i = 0; i < r.runs.size(); i++) {
+      memcpy(staged.data() + off, r.runs[i], size_t(r.run_buffers[i]) * c->buf_bytes);
+      off += size_t(r.run_buffers[i]) * c->buf_bytes;
+    }
+    compute(c, staged.data(), r.n, r);
+  }
   if (spectra_db && !r.spectra.empty()) memcpy(spectra_db, r.spectra.data(), r.spectra.size() * sizeof(float));
   if (hit_mask && !r.masks.empty()) memcpy(hit_mask, r.masks.data(), r.masks.size() * sizeof(uint32_t));
   if (hit_count) memcpy(hit_count, r.counts.data(), r.counts.size() * sizeof(uint32_t));

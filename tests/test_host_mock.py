@@ -102,27 +102,62 @@ def test_averaged_sweep_through_the_queue_terminates(tool):
 
 
 @pytest.mark.parametrize("threads", [1, 2])
-def test_zero_copy_batches_give_the_same_output(tool, tmp_path, threads):
-    """ProcessSamples::SetZeroCopy: batches submitted straight from the queue's slab (FIFO pool, contiguous runs)."""
-    zc = dict(ENV, SCN_ZERO_COPY="1")
-    for name in ("i8_dc_2048", "i16split_256", "f32_hann_1024", "i16_dc_512"):
-        case = next((c for c in GU.scan_cases(G) if c["name"] == name), None)
-        if case is None:
-            continue
-        a = sorted(GU.parse_hits(replay(tool, case, tmp_path, threads=threads, env=zc).stdout))
-        b = sorted(GU.parse_hits(case["text"]))
-        assert [f for f, _ in a] == [f for f, _ in b] and b
-    # a long averaged sweep wraps the slab several times: most batches are zero-copy, none is lost
-    r = subprocess.run([tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "600", "4",
-                        "7", str(threads), "4"], capture_output=True, text=True, timeout=300, env=zc)
+def test_staging_copy_and_slab_submits_give_the_same_output(tool, tmp_path, threads):
+    """Default: batches go to scn_submit_gather straight from the queue's slab (FIFO pool, address runs); with
+    SCN_STAGING_COPY the consumer packs every batch into a staging buffer first.  The mock reads the submitted
+    pointers only at collect time, so a message recycled before its ticket is collected would corrupt the output."""
+    staged = dict(ENV, SCN_STAGING_COPY="1")
+    for env in (ENV, staged):
+        for name in ("i8_dc_2048", "i16split_256", "f32_hann_1024", "i16_dc_512"):
+            case = next((c for c in GU.scan_cases(G) if c["name"] == name), None)
+            if case is None:
+                continue
+            a = sorted(GU.parse_hits(replay(tool, case, tmp_path, threads=threads, env=env).stdout))
+            b = sorted(GU.parse_hits(case["text"]))
+            assert [f for f, _ in a] == [f for f, _ in b] and b
+    # a long averaged sweep wraps the slab several times: most batches come straight from the slab, none is lost
+    args = [tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "600", "4", "7",
+            str(threads), "4"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300, env=ENV)
     assert r.returncode == 0, r.stderr[-2000:]
     m = re.search(r"buffers (\d+) hits (\d+) launches (\d+) zero-copy batches (\d+)", r.stderr)
     assert m and int(m.group(1)) == 3 * 3 * 600
     assert int(m.group(4)) > 0
-    base = subprocess.run([tool, "synth", "1", "1024", "20000000", "8", "1", "30.0", "2400000000.0", "2450000000.0", "600", "4",
-                           "7", str(threads), "4"], capture_output=True, text=True, timeout=300, env=ENV)
+    base = subprocess.run(args, capture_output=True, text=True, timeout=300, env=staged)
     m0 = re.search(r"buffers (\d+) hits (\d+) launches (\d+) zero-copy batches (\d+)", base.stderr)
     assert m0 and m0.group(1) == m.group(1) and m0.group(2) == m.group(2) and int(m0.group(4)) == 0
+
+
+@pytest.mark.parametrize("append_batch", [3, 64])
+def test_batched_appends_print_what_single_appends_print(tool, tmp_path, append_batch):
+    """SampleQueue::AppendSamplesBatch == that many AppendSamples calls: same first-sweep drop, same scan-start lines,
+    same sequence order, hence the reference's stdout (single worker: print order is sequence order)."""
+    env = dict(ENV, SCN_APPEND_BATCH=str(append_batch))
+    for case in GU.scan_cases(G):
+        if case["name"].startswith("i16split"):
+            continue                                         # the split layout has no batched form
+        if case["n"] < 256:
+            continue
+        got = replay(tool, case, tmp_path, threads=1, env=env).stdout
+        strip = lambda t: [re.sub(r"power_db .*|Max signal .*|Start scan at .*", "", l) for l in str(t).splitlines()
+                           if not re.match(r"Frequency \d+:|Starting source thread|Stopping source thread", l)]
+        assert strip(got) == strip(case["text"]), case["name"]
+
+
+def test_many_producers_batched_appends_lose_nothing(tool):
+    """Four producer threads x 64-buffer appends x two workers with a batch linger against one producer x
+    single appends: every buffer is processed once (same buffer and hit totals; K = 1 detection is order free)."""
+    def run(*extra):
+        r = subprocess.run([tool, "bench", "1", "2048", "8", "1", "64", "6000", *extra], capture_output=True, text=True,
+                           timeout=300, env=ENV)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"\((\d+) buffers .* (\d+) hits, (\d+) launches of which (\d+) straight", r.stdout)
+        assert m, r.stdout
+        return int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    base = run("1", "256", "1", "1", "0")
+    many = run("2", "256", "4", "64", "200")
+    assert base[0] == many[0] == 6000 and base[1] == many[1] and base[1] > 0
+    assert many[3] > 0
 
 
 def test_hackrf_sweep_replay(tool, tmp_path):
@@ -140,14 +175,16 @@ def test_hackrf_sweep_replay(tool, tmp_path):
     assert strip(r.stdout) == strip(want)
 
 
-def run_record(tool, tmp_path, prefix=()):
+def run_record(tool, tmp_path, prefix=(), averaging=1, pre_post=None):
     n, fs, enob, kind, dc, per_sweep, pre, post = [int(x) for x in GR["params"][:8]]
+    if pre_post is not None:
+        pre, post = pre_post
     thr = float(GR["params"][8])
     rp, fp = str(tmp_path / "raw.bin"), str(tmp_path / "freq.bin")
     GR["raw"].tofile(rp)
     GR["freqs"].astype(np.float64).tofile(fp)
     r = subprocess.run([*prefix, tool, "record", str(kind), str(n), repr(float(fs)), str(enob), str(dc), repr(thr), "5",
-                        str(per_sweep), rp, fp, str(tmp_path / "rec-"), str(pre), str(post), "1"],
+                        str(per_sweep), rp, fp, str(tmp_path / "rec-"), str(pre), str(post), "1", str(averaging)],
                        capture_output=True, text=True, timeout=300, env=ENV)
     assert r.returncode == 0, r.stderr[-2000:]
     return r
@@ -167,8 +204,26 @@ def test_recording_is_bit_identical_to_the_reference(tool, tmp_path):
         assert len(data) == size and hashlib.sha256(data).hexdigest() == sha
 
 
+def test_recording_window_closes_with_averaging(tool, tmp_path):
+    """K = 2, pre = post = 0 (the reference's defaults for multi-frequency scans): only ids 0, 2, 4, ... reach
+    ProcessWrite, so `sequenceId == end` (end = trigger + 1, odd) never holds; the window must still close, at the
+    end id, when the first later group arrives -- not run on to the end of the stream."""
+    r = run_record(tool, tmp_path, averaging=2, pre_post=(0, 0))
+    got = r.stdout.replace(str(tmp_path) + os.sep, "")
+    marks = [l for l in got.splitlines() if re.match(r"BeginWrite|EndWrite", l)]
+    begins = [int(l.rsplit(" ", 1)[1]) for l in marks if l.startswith("BeginWrite")]
+    ends = [int(l.split()[1]) for l in marks if l.startswith("EndWrite")]
+    # loud buffers carry sequence ids 5, 6, 7, 16, 25 -> groups (4,5) (6,7) | (16,17) | (24,25) trigger
+    assert begins == [4, 16, 24], marks
+    assert ends == [7, 17, 25], marks
+    assert [m.split()[0].rstrip(":") for m in marks] == ["BeginWrite", "EndWrite"] * 3, marks
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("rec-"))
+    # windows [4, 7), [16, 17), [24, 25) in sequence ids: 3 + 1 + 1 messages of 2048 fftwf_complex
+    assert [os.path.getsize(os.path.join(tmp_path, f)) for f in files] == [3 * 2048 * 8, 2048 * 8, 2048 * 8]
+
+
 def test_host_layer_is_clean_under_thread_sanitizer(tmp_path):
-    """Two workers + the producer + (record mode) the writer thread, with ThreadSanitizer watching the host code."""
+    """Two workers + the producer(s) + (record mode) the writer thread, with ThreadSanitizer watching the host code."""
     probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")],
                            input="int main(){return 0;}", capture_output=True, text=True)
     if probe.returncode != 0:
@@ -180,5 +235,9 @@ def test_host_layer_is_clean_under_thread_sanitizer(tmp_path):
     case = next(c for c in GU.scan_cases(G) if c["name"] == "i8_dc_2048")
     r1 = replay(tsan, case, tmp_path, threads=2, prefix=prefix)
     r2 = run_record(tsan, tmp_path, prefix=prefix)
-    for r in (r1, r2):
+    # four producer threads appending 64-buffer batches + two workers submitting straight from the slab + linger
+    r3 = subprocess.run([*prefix, tsan, "bench", "1", "2048", "8", "1", "64", "3000", "2", "256", "4", "64", "200"],
+                        capture_output=True, text=True, timeout=600, env=ENV)
+    assert r3.returncode == 0, r3.stderr[-2000:]
+    for r in (r1, r2, r3):
         assert "ThreadSanitizer" not in r.stderr and "ThreadSanitizer" not in r.stdout, (r.stderr + r.stdout)[-4000:]
