@@ -159,6 +159,12 @@ SCN_API int scn_submit_gather(scn_ctx* ctx, const void* const* runs, const uint3
 SCN_API int scn_collect(scn_ctx* ctx, uint32_t ticket, float* spectra_db, uint32_t* hit_mask,
                         uint32_t* hit_count, scn_hit* hits, float* td_max_min);
 
+/* scn_collect without the copies: waits for the ticket and returns POINTERS into the slot's pinned host buffers
+ * (layouts as above; NULL for outputs the context does not produce).  They stay valid until the slot is reused, i.e.
+ * until the ticket_slots-th scn_submit after the one that returned `ticket`. */
+SCN_API int scn_collect_view(scn_ctx* ctx, uint32_t ticket, const uint32_t** hit_mask, const uint32_t** hit_count,
+                             const scn_hit** hits, const float** td_max_min);
+
 /* ---- Device-resident path ---------------------------------------------------
  * All pointers are device pointers on ctx's device (16-byte aligned raw); outputs nullable as
  * above.  Enqueues exactly one fused kernel on `stream` (a cudaStream_t, NULL == default
@@ -213,9 +219,23 @@ SCN_API int scn_exchange_connect_ipc(scn_exchange* x, const unsigned char* handl
 SCN_API int scn_exchange_connect_local(scn_exchange* const* all /* [world], index == rank */, uint32_t world);
 SCN_API int scn_exchange_publish(scn_exchange* x, const uint32_t* d_records, void* stream, uint64_t* seq_out);
 SCN_API int scn_exchange_merge(scn_exchange* x, uint64_t seq, uint32_t* d_merged, void* stream);
+/* host-pointer forms (synchronous): upload + publish; wait + merge + download */
+SCN_API int scn_exchange_publish_host(scn_exchange* x, const uint32_t* host_records, uint64_t* seq_out);
+SCN_API int scn_exchange_merge_host(scn_exchange* x, uint64_t seq, uint32_t* host_merged);
 SCN_API int scn_exchange_status(scn_exchange* x, uint32_t* timed_out_seq);
 SCN_API uint32_t scn_exchange_slots(void);
 SCN_API int scn_exchange_destroy(scn_exchange* x);
+
+/* ---- In-process NCCL gather of the per-step records (scn_nccl.cu) -----------------------
+ * One process driving several GPUs (csrc/host/sweepProcessor.cpp): ncclCommInitAll over `devices`, then per sweep
+ * one grouped ncclAllGather of every device's partial record table [n_steps][record_words] over NVLink and the merge
+ * kernel on every device.  host_partials[d] is device d's table (host memory); host_merged receives the merged
+ * table (every device ends up with the same one; they are compared).  NCCL is dlopen'ed at the first call. */
+typedef struct scn_gather scn_gather;
+SCN_API int scn_nccl_gather_create(const int* devices, uint32_t n_devices, uint32_t n_steps, uint32_t record_words,
+                                   scn_gather** out);
+SCN_API int scn_nccl_gather_merge_host(scn_gather* g, const uint32_t* const* host_partials, uint32_t* host_merged);
+SCN_API int scn_nccl_gather_destroy(scn_gather* g);
 
 /* ---- Standalone sample conversion (replaces Utility::*_to_float_complex, utility.cpp:9-84, as called by
  * MessageQueue::AppendSamples, messageQueue.h:190-237) -------------------------------------------------

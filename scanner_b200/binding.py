@@ -66,6 +66,7 @@ SYMBOLS = [
     ("scn_submit", _I, [_VP, _VP, _U32, C.POINTER(_U32)]),
     ("scn_submit_gather", _I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _U32, _U32, C.POINTER(_U32)]),
     ("scn_collect", _I, [_VP, _U32, _VP, _VP, _VP, _VP, _VP]),
+    ("scn_collect_view", _I, [_VP, _U32, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("scn_launch_device", _I, [_VP, _VP, _U32, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("scn_launch_count", _U64, [_VP]),
     ("scn_kernel_name", C.c_char_p, [_VP]),
@@ -79,6 +80,11 @@ SYMBOLS = [
     ("scn_exchange_connect_local", _I, [C.POINTER(_VP), _U32]),
     ("scn_exchange_publish", _I, [_VP, _VP, _VP, C.POINTER(_U64)]),
     ("scn_exchange_merge", _I, [_VP, _U64, _VP, _VP]),
+    ("scn_exchange_publish_host", _I, [_VP, _VP, C.POINTER(_U64)]),
+    ("scn_exchange_merge_host", _I, [_VP, _U64, _VP]),
+    ("scn_nccl_gather_create", _I, [C.POINTER(_I), _U32, _U32, _U32, C.POINTER(_VP)]),
+    ("scn_nccl_gather_merge_host", _I, [_VP, C.POINTER(_VP), _VP]),
+    ("scn_nccl_gather_destroy", _I, [_VP]),
     ("scn_exchange_status", _I, [_VP, C.POINTER(_U32)]),
     ("scn_exchange_slots", _U32, []),
     ("scn_exchange_destroy", _I, [_VP]),

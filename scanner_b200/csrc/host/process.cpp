@@ -117,9 +117,10 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   } slot[2];
   for (auto& s : slot)
     if (scn_alloc_pinned(bufBytes * size_t(maxSpectra) * K, &s.staging) != SCN_OK) Die("scn_alloc_pinned");
-  std::vector<uint32_t> counts(maxSpectra);
-  std::vector<scn_hit> hits(m_mode == FrequencyDomain ? size_t(maxSpectra) * cap : 0);
-  std::vector<float> tdmm(m_mode == TimeDomain ? size_t(maxSpectra) * 2 : 0);
+  // results are read in place from the ticket's pinned buffers (scn_collect_view): no copy of counts / hit records
+  const uint32_t* counts = nullptr;
+  const scn_hit* hits = nullptr;
+  const float* tdmm = nullptr;
 
   const bool zeroCopy = m_zeroCopy && q->IsPinnedSlab();
   // What a batch is submitted from.  The messages live in ONE pinned slab and the pool recycles first-in first-out,
@@ -167,10 +168,9 @@ void ProcessSamples::ThreadWorker(uint32_t threadId) {
   auto finish = [&](InFlight& f) {
     const uint32_t nSpectra = f.nSpectra;
     if (nSpectra) {
-      if (scn_collect(ctx, f.ticket, nullptr, nullptr, counts.data(), hits.empty() ? nullptr : hits.data(),
-                      tdmm.empty() ? nullptr : tdmm.data()) != SCN_OK)
-        Die("scn_collect");
-      std::lock_guard<std::mutex> lock(g_printMutex);
+      if (scn_collect_view(ctx, f.ticket, nullptr, &counts, &hits, &tdmm) != SCN_OK) Die("scn_collect_view");
+      std::unique_lock<std::mutex> lock(g_printMutex, std::defer_lock);
+      if (m_out || m_sink || !m_fileNameBase.empty()) lock.lock();   // output order and the trigger/record bookkeeping
       for (uint32_t s = 0; s < nSpectra; s++) {
         // the first message of the group carries the spectrum's identity
         SampleQueue::MessageHeader& header = f.batch[size_t(s) * K]->GetHeader();

@@ -40,6 +40,13 @@ SampleQueue::SampleQueue(SampleKind kind, uint32_t enob, uint32_t sampleCount, u
     m.m_header = MessageHeader{MessageHeader::Free, 0, 0.0, 0, 0};
     m_free.push_back(&m);
   }
+  // Ring mode needs every message to come back in bounded time; the recording history parks messages for as long
+  // as a window is open, so a recording queue keeps the free list.
+  if (!doWrite) {
+    m_ring = true;
+    m_ringFree.assign(poolCount, 1);
+    m_free.clear();
+  }
   if (doWrite) {
     printf("Starting write thread...\n");                            // messageQueue.h:164-168
     m_writeThread.reset(new std::thread(&SampleQueue::WriteThreadWorker, this));
@@ -74,8 +81,32 @@ bool SampleQueue::AcceptOrDrop(time_t time) {
   return true;
 }
 
+// Ring mode (SetFifoPool without recording): the slab is handed out strictly in address order, wrapping, and a
+// message becomes available again when the ring head reaches it after it was freed.  Whatever order the consumers
+// finish their batches in, consecutive appends therefore ALWAYS land in consecutive slab slots: a drained batch is
+// one address run (two at the wrap) for ever -- a FIFO free list fragments a little more with every batch that two
+// workers return out of order.  The price is head-of-line blocking on the oldest unfreed message, which the
+// consumers' in-order batches make a non-issue.  Caller holds m_poolMutex; returns how many were taken (>= 1).
+size_t SampleQueue::TakeFromRing(std::unique_lock<std::mutex>& lock, size_t want, std::vector<MessageType*>* out,
+                                 std::deque<MessageType*>* cache) {
+  m_poolAvailable.wait(lock, [this] { return m_ringFree[m_ringHead] != 0; });
+  size_t got = 0;
+  while (got < want && m_ringFree[m_ringHead]) {
+    m_ringFree[m_ringHead] = 0;
+    MessageType* m = &m_messages[m_ringHead];
+    if (out) out->push_back(m); else cache->push_back(m);
+    m_ringHead = (m_ringHead + 1 == m_messages.size()) ? 0 : m_ringHead + 1;
+    got++;
+  }
+  return got;
+}
+
 SampleQueue::MessageType* SampleQueue::Allocate() {
-  if (m_allocCache.empty()) {                                    // caller holds m_allocMutex
+  if (m_allocCache.empty() && m_ring) {                          // caller holds m_allocMutex
+    std::unique_lock<std::mutex> lock(m_poolMutex);
+    TakeFromRing(lock, kAllocChunk, nullptr, &m_allocCache);
+  }
+  if (m_allocCache.empty()) {
     std::unique_lock<std::mutex> lock(m_poolMutex);
     m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
     for (size_t i = 0; i < kAllocChunk && !m_free.empty(); i++) {
@@ -96,8 +127,9 @@ SampleQueue::MessageType* SampleQueue::Allocate() {
 void SampleQueue::Free(MessageType* m) {
   std::unique_lock<std::mutex> lock(m_poolMutex);
   m->m_header.m_kind = MessageHeader::Free;
-  m_free.push_back(m);
-  m_poolAvailable.notify_one();
+  if (m_ring) m_ringFree[size_t(m - m_messages.data())] = 1;
+  else m_free.push_back(m);
+  m_poolAvailable.notify_all();
 }
 
 // `count` free messages, oldest first in FIFO mode so that they form as few address runs as possible.
@@ -111,6 +143,10 @@ void SampleQueue::AllocateMany(uint32_t count, std::vector<MessageType*>& out) {
     }
     if (out.size() == count) break;
     std::unique_lock<std::mutex> lock(m_poolMutex);
+    if (m_ring) {
+      TakeFromRing(lock, count - out.size(), &out, nullptr);
+      continue;
+    }
     m_poolAvailable.wait(lock, [this] { return !m_free.empty(); });
     while (!m_free.empty() && out.size() < count) {
       if (m_fifoPool) { out.push_back(m_free.front()); m_free.pop_front(); }
@@ -235,6 +271,7 @@ SampleQueue::MessageType* SampleQueue::GetNextSamples() {
 }
 
 void SampleQueue::SetFifoPool(bool fifo) {
+  // only meaningful for a recording queue (free-list mode); a ring-mode queue is always in address order
   std::unique_lock<std::mutex> cacheLock(m_allocMutex);
   std::unique_lock<std::mutex> lock(m_poolMutex);
   m_fifoPool = fifo;
@@ -309,7 +346,8 @@ void SampleQueue::MessageProcessed(const std::vector<MessageType*>& messages) {
     for (MessageType* m : messages) {
       assert(m->m_header.m_kind != MessageHeader::Illegal);
       m->m_header.m_kind = MessageHeader::Free;
-      m_free.push_back(m);
+      if (m_ring) m_ringFree[size_t(m - m_messages.data())] = 1;
+      else m_free.push_back(m);
     }
     m_poolAvailable.notify_all();
     return;

@@ -96,8 +96,10 @@ class SampleQueue {
   uint32_t GetNextBatch(std::vector<MessageType*>& out, uint32_t maxCount, uint32_t multiple = 1,
                         bool wait = true, bool contiguous = false, uint32_t minCount = 0,
                         uint32_t maxWaitMicros = 0);
-  // Recycle messages first-in first-out (ascending slab addresses) instead of last-in first-out, so consecutive
-  // appends land in consecutive slab slots.  Off by default; ProcessSamples::SetZeroCopy turns it on.
+  // A queue that does not record hands its slab out in address order (a ring, see TakeFromRing in the .cpp), so
+  // consecutive appends land in consecutive slab slots and a drained batch is one address run.  A recording queue
+  // (doWrite) parks messages in its history, so it keeps a free list; SetFifoPool(true) makes that list first-in
+  // first-out (ascending addresses while nothing is parked) instead of most-recently-freed first.
   void SetFifoPool(bool fifo);
   bool IsPinnedSlab() const { return m_slab != nullptr; }
   void MessageProcessed(MessageType* message);
@@ -175,6 +177,12 @@ class SampleQueue {
   std::vector<MessageType> m_messages;
   std::deque<MessageType*> m_free;
   bool m_fifoPool = false;
+  // ring mode (see TakeFromRing): which messages are free, and the next slab slot to hand out
+  bool m_ring = false;
+  std::vector<uint8_t> m_ringFree;
+  size_t m_ringHead = 0;
+  size_t TakeFromRing(std::unique_lock<std::mutex>& lock, size_t want, std::vector<MessageType*>* out,
+                      std::deque<MessageType*>* cache);
   // free messages the appending side has already taken out of the pool (refilled kAllocChunk at a time, so the
   // producer touches the contended pool mutex once per chunk instead of once per buffer)
   static const size_t kAllocChunk = 32;

@@ -148,10 +148,16 @@ void ReplaySource::Append(SampleQueue* q, size_t b) {
 }
 
 bool ReplaySource::GetNextSamples(SampleQueue* sampleQueue, double_t& centerFrequency) {
+  if (m_repeatTotal) {                       // capture ring: wrap until the requested total has been streamed
+    if (m_streamed >= m_repeatTotal || m_isDone || m_nBuffers == 0) return false;
+    if (m_next >= m_nBuffers) m_next = 0;
+  }
   if (m_next >= m_nBuffers || m_isDone) return false;
   centerFrequency = m_frequencies[m_next];
   if (m_appendBatch > 1 && m_kind != SampleQueue::Short) {
-    const size_t n = m_nBuffers - m_next < m_appendBatch ? m_nBuffers - m_next : m_appendBatch;
+    size_t n = m_nBuffers - m_next < m_appendBatch ? m_nBuffers - m_next : m_appendBatch;
+    if (m_repeatTotal && m_repeatTotal - m_streamed < n) n = size_t(m_repeatTotal - m_streamed);
+    m_streamed += n;
     const time_t* times = nullptr;
     if (m_buffersPerSweep) {
       m_times.assign(n, 0);
@@ -163,6 +169,7 @@ bool ReplaySource::GetNextSamples(SampleQueue* sampleQueue, double_t& centerFreq
     m_next += n;
     return true;
   }
+  m_streamed++;
   Append(sampleQueue, m_next++);
   return true;
 }
@@ -172,6 +179,12 @@ bool ReplaySource::StartStreaming(uint32_t numIterations, SampleQueue& sampleQue
 }
 
 void ReplaySource::ThreadWorker() {
+  if (m_localCopy) {
+    m_local.assign(m_raw, m_raw + m_nBuffers * m_bufferBytes);
+    m_localFrequencies.assign(m_frequencies, m_frequencies + m_nBuffers);
+    m_raw = m_local.data();
+    m_frequencies = m_localFrequencies.data();
+  }
   double_t f;
   while (GetNextSamples(m_sampleQueue, f)) {}
 }

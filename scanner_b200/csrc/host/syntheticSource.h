@@ -52,11 +52,20 @@ class ReplaySource : public SignalSource {
   // a whole USB transfer at once (hackRFSource.cpp:251-264: 64 buffers per 262 144-byte transfer); 1 == one
   // AppendSamples call per buffer.  Interleaved kinds only.
   void SetAppendBatch(uint32_t n) { m_appendBatch = n ? n : 1; }
+  // Stream `totalBuffers` buffers by cycling over the recorded ones (a capture ring replayed for as long as asked).
+  void SetRepeat(uint64_t totalBuffers) { m_repeatTotal = totalBuffers; }
+  // Copy the recording into memory first touched by the producer thread itself before streaming from it (keeps the
+  // source side of the hand-off's memcpy local to the core that runs it on multi-socket hosts).
+  void SetLocalCopy(bool on) { m_localCopy = on; }
 
  private:
   void Append(SampleQueue* q, size_t b);
   uint32_t m_appendBatch = 1;
   std::vector<time_t> m_times;
+  uint64_t m_repeatTotal = 0, m_streamed = 0;
+  bool m_localCopy = false;
+  std::vector<char> m_local;
+  std::vector<double> m_localFrequencies;
   SampleQueue::SampleKind m_kind;
   const char* m_raw;
   const double* m_frequencies;

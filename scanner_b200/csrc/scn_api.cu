@@ -716,6 +716,22 @@ SCN_API int scn_collect(scn_ctx* c, uint32_t ticket, float* spectra_db, uint32_t
   return SCN_OK;
 }
 
+SCN_API int scn_collect_view(scn_ctx* c, uint32_t ticket, const uint32_t** hit_mask, const uint32_t** hit_count,
+                             const scn_hit** hits, const float** td_max_min) {
+  if (!c) return fail(SCN_ERR_INVALID, "ctx is NULL");
+  if (ticket >= c->slots.size() || !c->slots[ticket].busy)
+    return fail(SCN_ERR_INVALID, "ticket %u is not in flight", ticket);
+  Slot& s = c->slots[ticket];
+  SCN_CUDA(cudaSetDevice(c->cfg.device));
+  SCN_CUDA(cudaEventSynchronize(s.done));
+  if (hit_mask) *hit_mask = s.h_masks;
+  if (hit_count) *hit_count = s.h_counts;
+  if (hits) *hits = s.h_hits;
+  if (td_max_min) *td_max_min = s.h_td;
+  s.busy = false;
+  return SCN_OK;
+}
+
 SCN_API int scn_process_host(scn_ctx* c, const void* raw, uint32_t n_spectra, float* spectra_db,
                              uint32_t* hit_mask, uint32_t* hit_count, scn_hit* hits, float* td_max_min) {
   if (!c) return fail(SCN_ERR_INVALID, "ctx is NULL");

@@ -53,6 +53,8 @@ struct scn_exchange {
   std::vector<bool> ipc_opened;
   uint32_t** d_peer = nullptr;                // device copy of peer[]
   uint32_t* d_error = nullptr;                // set by a merge that gave up waiting
+  uint32_t* d_scratch = nullptr;              // staging of the host-pointer forms
+  uint32_t* d_scratch2 = nullptr;
   uint64_t seq = 0;                           // last published sequence number
   bool connected = false;
 };
@@ -248,6 +250,33 @@ SCN_API int scn_exchange_merge(scn_exchange* x, uint64_t seq, uint32_t* d_merged
   return SCN_OK;
 }
 
+// Host-pointer forms for callers that keep their partial records on the host (csrc/host/sweepProcessor.cpp):
+// upload + publish, and merge + download (synchronous).
+SCN_API int scn_exchange_publish_host(scn_exchange* x, const uint32_t* host_records, uint64_t* seq_out) {
+  if (!x || !host_records) return scn::api_fail(SCN_ERR_INVALID, "exchange_publish_host: NULL argument");
+  SCN_XCUDA(cudaSetDevice(x->device));
+  if (!x->d_scratch) SCN_XCUDA(cudaMalloc(&x->d_scratch, sizeof(uint32_t) * x->rec_total));
+  SCN_XCUDA(cudaMemcpy(x->d_scratch, host_records, sizeof(uint32_t) * x->rec_total, cudaMemcpyHostToDevice));
+  int rc = scn_exchange_publish(x, x->d_scratch, nullptr, seq_out);
+  if (rc != SCN_OK) return rc;
+  SCN_XCUDA(cudaStreamSynchronize(nullptr));       // the scratch is reused by the next call
+  return SCN_OK;
+}
+
+SCN_API int scn_exchange_merge_host(scn_exchange* x, uint64_t seq, uint32_t* host_merged) {
+  if (!x || !host_merged) return scn::api_fail(SCN_ERR_INVALID, "exchange_merge_host: NULL argument");
+  SCN_XCUDA(cudaSetDevice(x->device));
+  if (!x->d_scratch2) SCN_XCUDA(cudaMalloc(&x->d_scratch2, sizeof(uint32_t) * x->rec_total));
+  int rc = scn_exchange_merge(x, seq, x->d_scratch2, nullptr);
+  if (rc != SCN_OK) return rc;
+  SCN_XCUDA(cudaMemcpy(host_merged, x->d_scratch2, sizeof(uint32_t) * x->rec_total, cudaMemcpyDeviceToHost));
+  uint32_t bad = 0;
+  rc = scn_exchange_status(x, &bad);
+  if (rc != SCN_OK) return rc;
+  if (bad) return scn::api_fail(SCN_ERR_CUDA, "exchange_merge_host: gave up waiting for a peer to publish sequence %u", bad);
+  return SCN_OK;
+}
+
 SCN_API int scn_exchange_status(scn_exchange* x, uint32_t* timed_out_seq) {
   if (!x || !timed_out_seq) return scn::api_fail(SCN_ERR_INVALID, "exchange_status: NULL argument");
   SCN_XCUDA(cudaSetDevice(x->device));
@@ -264,6 +293,8 @@ SCN_API int scn_exchange_destroy(scn_exchange* x) {
   for (uint32_t r = 0; r < x->world; r++)
     if (r < x->ipc_opened.size() && x->ipc_opened[r] && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
   if (x->d_peer) cudaFree(x->d_peer);
+  if (x->d_scratch) cudaFree(x->d_scratch);
+  if (x->d_scratch2) cudaFree(x->d_scratch2);
   if (x->d_error) cudaFree(x->d_error);
   if (x->window) cudaFree(x->window);
   delete x;

@@ -28,6 +28,7 @@
 #include "process.h"
 #include "sampleBuffer.h"
 #include "sampleQueue.h"
+#include "sweepProcessor.h"
 #include "syntheticSource.h"
 
 static std::vector<char> ReadFile(const char* path) {
@@ -191,6 +192,48 @@ int main(int argc, char** argv) {
             (unsigned long)process.GetZeroCopyBatches());
     return 0;
   }
+  if (cmd == "sweep" && argc >= 14) {
+    // scan_b200 sweep <kind> <N> <fs> <enob> <dc> <threshold> <start> <stop> <buffers_per_step> <iterations> <seed>
+    //                 <gpus> [averaging] [nccl|peer] [report]
+    // The synth scan through SweepProcessor: one worker per GPU, retune steps split across them, per-sweep records
+    // exchanged with NCCL (default) or the NVLink peer-memory windows.  Prints what `synth` prints, whatever <gpus>.
+    const int kind = atoi(argv[2]);
+    const uint32_t n = atoi(argv[3]), fs = uint32_t(atof(argv[4])), enob = atoi(argv[5]);
+    const bool dc = atoi(argv[6]) != 0;
+    const float thr = float(atof(argv[7]));
+    const double start = atof(argv[8]), stop = atof(argv[9]);
+    const uint32_t perStep = atoi(argv[10]), iterations = atoi(argv[11]);
+    const uint64_t seed = strtoull(argv[12], nullptr, 0);
+    const uint32_t gpus = atoi(argv[13]) > 0 ? atoi(argv[13]) : 1;
+    const uint32_t averaging = argc > 14 ? atoi(argv[14]) : 1;
+    const bool peer = argc > 15 && std::string(argv[15]) == "peer";
+    const bool report = argc > 16 && atoi(argv[16]) != 0;
+    SyntheticSource source(SampleQueue::SampleKind(kind), enob, seed, perStep, fs, n, start, stop);
+    std::vector<double> steps(scn_frequency_table(fs, start, stop, 0.75, 0.0, nullptr, 0));
+    scn_frequency_table(fs, start, stop, 0.75, 0.0, steps.data(), uint32_t(steps.size()));
+    std::vector<int> devices(gpus);
+    for (uint32_t d = 0; d < gpus; d++) devices[d] = int(d);
+    SweepProcessor process(n, fs, enob, thr, SCN_WIN_BLACKMAN_HARRIS, steps, devices,
+                           peer ? SweepProcessor::PeerMemory : SweepProcessor::NcclAllGather);
+    process.SetAveraging(averaging);
+    process.SetSweepReport(report);
+    SampleQueue queue(SampleQueue::SampleKind(kind), enob, n, 1024, dc, false);
+    const auto t0 = std::chrono::steady_clock::now();
+    source.Start();
+    source.StartStreaming(iterations, queue);
+    process.StartProcessing(queue);
+    source.Join();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    printf("Elapsed time = %f ms\n", ms);
+    fprintf(stderr, "buffers %lu hits %lu launches %lu sweeps %u per-gpu", (unsigned long)process.GetBuffersProcessed(),
+            (unsigned long)process.GetHitCount(), (unsigned long)process.GetLaunchCount(), process.GetSweepCount());
+    for (uint32_t d = 0; d < gpus; d++) fprintf(stderr, " %lu", (unsigned long)process.GetBuffersOnDevice(d));
+    uint64_t recHits = 0, recSpectra = 0;
+    const std::vector<uint32_t>& rec = process.GetLastSweepRecords();
+    for (size_t s = 0; s * (n / 32 + 2) < rec.size(); s++) { recHits += rec[s * (n / 32 + 2)]; recSpectra += rec[s * (n / 32 + 2) + 1]; }
+    fprintf(stderr, " last-sweep-records hits %lu spectra %lu\n", (unsigned long)recHits, (unsigned long)recSpectra);
+    return 0;
+  }
   if (cmd == "bench" && argc >= 8) {
     // scan_b200 bench <kind> <N> <enob> <dc> <distinct_buffers> <total_buffers> [threads] [max_batch] [producers]
     //                 [append_batch] [linger_us]
@@ -213,18 +256,23 @@ int main(int argc, char** argv) {
       SyntheticSource gen(SampleQueue::SampleKind(kind), enob ? enob : 12, 1234, 1, fs, n, 2.4e9, 0.0);
       for (size_t b = 0; b < distinct; b++) gen.Generate(0, 0, uint32_t(b), pool.data() + b * bb);
     }
-    std::vector<char> raw(total * bb);
-    std::vector<double> freqs(total);
-    for (size_t b = 0; b < total; b++) {
+    // every producer replays its own capture ring (>= 128 MB: far beyond the CPU caches, so the hand-off's memcpy
+    // reads DRAM as it would behind a USB/PCIe DMA), copied into memory the producer thread touches first
+    size_t ringBuffers = (size_t(128) << 20) / bb;
+    if (ringBuffers > total / producers) ringBuffers = total / producers ? total / producers : 1;
+    std::vector<char> raw(ringBuffers * bb);
+    std::vector<double> freqs(ringBuffers);
+    for (size_t b = 0; b < ringBuffers; b++) {
       memcpy(raw.data() + b * bb, pool.data() + (b % distinct) * bb, bb);
       freqs[b] = 2.4075e9 + 15e6 * double(b % 50);
     }
     std::vector<std::unique_ptr<ReplaySource>> sources;
     for (uint32_t pr = 0; pr < producers; pr++) {
-      const size_t b0 = total * pr / producers, b1 = total * (pr + 1) / producers;
-      sources.emplace_back(new ReplaySource(SampleQueue::SampleKind(kind), raw.data() + b0 * bb, freqs.data() + b0,
-                                            b1 - b0, 0, fs, n));
+      const size_t share = total * (pr + 1) / producers - total * pr / producers;
+      sources.emplace_back(new ReplaySource(SampleQueue::SampleKind(kind), raw.data(), freqs.data(), ringBuffers, 0, fs, n));
       sources.back()->SetAppendBatch(appendBatch);
+      sources.back()->SetRepeat(share);
+      sources.back()->SetLocalCopy(true);
     }
     ProcessSamples process(n, fs, enob, 25.0f, SCN_WIN_BLACKMAN_HARRIS, ProcessSamples::FrequencyDomain, threads);
     process.SetOutput(nullptr);

@@ -162,6 +162,18 @@ int scn_collect(scn_ctx* c, uint32_t ticket, float* spectra_db, uint32_t* hit_ma
   return SCN_OK;
 }
 
+int scn_collect_view(scn_ctx* c, uint32_t ticket, const uint32_t** hit_mask, const uint32_t** hit_count,
+                     const scn_hit** hits, const float** td_max_min) {
+  int rc = scn_collect(c, ticket, nullptr, nullptr, nullptr, nullptr, nullptr);    // computes into the slot
+  if (rc != SCN_OK) return rc;
+  Result& r = c->slots[ticket];
+  if (hit_mask) *hit_mask = r.masks.empty() ? nullptr : r.masks.data();
+  if (hit_count) *hit_count = r.counts.data();
+  if (hits) *hits = r.hits.empty() ? nullptr : r.hits.data();
+  if (td_max_min) *td_max_min = r.tdmm.empty() ? nullptr : r.tdmm.data();
+  return SCN_OK;
+}
+
 int scn_process_host(scn_ctx* c, const void* raw, uint32_t n_spectra, float* spectra_db, uint32_t* hit_mask,
                      uint32_t* hit_count, scn_hit* hits, float* td_max_min) {
   if (!c || (n_spectra && !raw)) return fail(SCN_ERR_INVALID, "process_host: bad arguments");
@@ -195,4 +207,71 @@ uint32_t scn_frequency_table(uint32_t fs, double start, double stop, double use_
   return orc_frequency_table(fs, start, stop, use_bw, dc_ignore, out, cap);
 }
 int scn_window_build(int type, uint32_t n, float* out) { orc_window_build(type, n, out); return SCN_OK; }
+
+void scn_shard_steps(uint32_t n_steps, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* end) {
+  if (world == 0) world = 1;
+  if (begin) *begin = uint32_t(uint64_t(n_steps) * rank / world);
+  if (end) *end = uint32_t(uint64_t(n_steps) * (rank + 1) / world);
+}
+}  // extern "C"
+
+// ---- record exchange / NCCL gather stand-ins (csrc/host/sweepProcessor.cpp): plain host memory, same semantics ----
+struct scn_exchange {
+  uint32_t rank, world, rec_total, rec_words;
+  uint64_t seq = 0;
+  std::vector<scn_exchange*> peers;
+  std::vector<std::vector<uint32_t>> rows[4];     // [slot][rank] -> that rank's table
+  std::vector<uint64_t> flags[4];
+};
+struct scn_gather { uint32_t n_devices, rec_total, rec_words; };
+static void merge_rows(const uint32_t* const* parts, uint32_t n_parts, uint32_t total, uint32_t rec_words, uint32_t* out) {
+  for (uint32_t x = 0; x < total; x++) {
+    uint32_t v = 0;
+    for (uint32_t p = 0; p < n_parts; p++) v = (x % rec_words) < 2 ? v + parts[p][x] : (v | parts[p][x]);
+    out[x] = v;
+  }
+}
+extern "C" {
+int scn_exchange_create(int, uint32_t rank, uint32_t world, uint32_t n_steps, uint32_t record_words, scn_exchange** out) {
+  scn_exchange* x = new scn_exchange();
+  x->rank = rank; x->world = world; x->rec_words = record_words; x->rec_total = n_steps * record_words;
+  for (int sl = 0; sl < 4; sl++) { x->rows[sl].assign(world, std::vector<uint32_t>(x->rec_total, 0u)); x->flags[sl].assign(world, 0); }
+  x->peers.assign(world, nullptr);
+  x->peers[rank] = x;
+  *out = x;
+  return SCN_OK;
+}
+int scn_exchange_connect_local(scn_exchange* const* all, uint32_t world) {
+  for (uint32_t a = 0; a < world; a++) all[a]->peers.assign(all, all + world);
+  return SCN_OK;
+}
+int scn_exchange_publish_host(scn_exchange* x, const uint32_t* host_records, uint64_t* seq_out) {
+  const uint64_t seq = ++x->seq;
+  for (scn_exchange* p : x->peers) {
+    if (!p) return fail(SCN_ERR_INVALID, "exchange: peers are not connected");
+    p->rows[seq % 4][x->rank].assign(host_records, host_records + x->rec_total);
+    p->flags[seq % 4][x->rank] = seq;
+  }
+  if (seq_out) *seq_out = seq;
+  return SCN_OK;
+}
+int scn_exchange_merge_host(scn_exchange* x, uint64_t seq, uint32_t* host_merged) {
+  std::vector<const uint32_t*> parts;
+  for (uint32_t r = 0; r < x->world; r++) {
+    if (x->flags[seq % 4][r] != seq) return fail(SCN_ERR_CUDA, "exchange: rank %u has not published %llu", r, (unsigned long long)seq);
+    parts.push_back(x->rows[seq % 4][r].data());
+  }
+  merge_rows(parts.data(), x->world, x->rec_total, x->rec_words, host_merged);
+  return SCN_OK;
+}
+int scn_exchange_destroy(scn_exchange* x) { delete x; return SCN_OK; }
+int scn_nccl_gather_create(const int*, uint32_t n_devices, uint32_t n_steps, uint32_t record_words, scn_gather** out) {
+  *out = new scn_gather{n_devices, n_steps * record_words, record_words};
+  return SCN_OK;
+}
+int scn_nccl_gather_merge_host(scn_gather* g, const uint32_t* const* host_partials, uint32_t* host_merged) {
+  merge_rows(host_partials, g->n_devices, g->rec_total, g->rec_words, host_merged);
+  return SCN_OK;
+}
+int scn_nccl_gather_destroy(scn_gather* g) { delete g; return SCN_OK; }
 }

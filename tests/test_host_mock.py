@@ -148,7 +148,7 @@ def test_many_producers_batched_appends_lose_nothing(tool):
     """Four producer threads x 64-buffer appends x two workers with a batch linger against one producer x
     single appends: every buffer is processed once (same buffer and hit totals; K = 1 detection is order free)."""
     def run(*extra):
-        r = subprocess.run([tool, "bench", "1", "2048", "8", "1", "64", "6000", *extra], capture_output=True, text=True,
+        r = subprocess.run([tool, "bench", "1", "2048", "8", "1", "64", "6144", *extra], capture_output=True, text=True,
                            timeout=300, env=ENV)
         assert r.returncode == 0, r.stderr[-2000:]
         m = re.search(r"\((\d+) buffers .* (\d+) hits, (\d+) launches of which (\d+) straight", r.stdout)
@@ -156,8 +156,71 @@ def test_many_producers_batched_appends_lose_nothing(tool):
         return int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))
     base = run("1", "256", "1", "1", "0")
     many = run("2", "256", "4", "64", "200")
-    assert base[0] == many[0] == 6000 and base[1] == many[1] and base[1] > 0
+    assert base[0] == many[0] == 6144 and base[1] == many[1] and base[1] > 0
     assert many[3] > 0
+
+
+def sweep_args(gpus, averaging=1, exchange="nccl", report=0, per_step=12, iterations=4):
+    # int8 IQ, N = 1024, 2.40 - 2.52 GHz at 20 MS/s: 8 retune steps; threshold low enough for plenty of hits
+    return ["1", "1024", "20000000", "8", "1", "17.0", "2400000000.0", "2520000000.0", str(per_step), str(iterations), "7",
+            str(gpus), str(averaging), exchange, str(report)]
+
+
+def scan_lines(text):
+    return [re.sub(r"Start scan at .*", "Start scan at <wall clock>", l) for l in text.splitlines()
+            if not re.match(r"(Starting|Stopped) process thread|Starting source thread|Stopping source thread|Frequency \d+:|Elapsed time", l)]
+
+
+@pytest.mark.parametrize("averaging", [1, 4])
+def test_sweep_processor_prints_the_single_gpu_output_on_any_gpu_count(tool, averaging):
+    """SweepProcessor (one worker per GPU, retune steps split across them, ordered emitter) against ProcessSamples with
+    one worker: the same lines in the same order for 1, 2, 3 and 8 GPUs (the mock ABI stands in for the devices), with
+    either record exchange; and the merged per-step records account for every spectrum and hit of the last sweep."""
+    base = subprocess.run([tool, "synth", *sweep_args(0, averaging)[:11], "1", str(averaging)], capture_output=True, text=True,
+                          timeout=300, env=ENV)
+    assert base.returncode == 0, base.stderr[-2000:]
+    want = scan_lines(base.stdout)
+    assert sum(l.startswith("freq ") for l in want) > 50 and sum(l.startswith("Start scan") for l in want) == 3
+    total = int(re.search(r"buffers (\d+) hits (\d+)", base.stderr).group(1))
+    for gpus, exchange in ((1, "nccl"), (2, "nccl"), (3, "peer"), (8, "nccl"), (8, "peer")):
+        r = subprocess.run([tool, "sweep", *sweep_args(gpus, averaging, exchange)], capture_output=True, text=True,
+                           timeout=300, env=ENV)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert scan_lines(r.stdout) == want, (gpus, exchange)
+        m = re.search(r"buffers (\d+) hits (\d+) launches (\d+) sweeps (\d+) per-gpu((?: \d+)+) last-sweep-records hits (\d+) "
+                      r"spectra (\d+)", r.stderr)
+        assert m, r.stderr
+        per_gpu = [int(x) for x in m.group(5).split()]
+        assert int(m.group(1)) == total == sum(per_gpu) and len(per_gpu) == gpus
+        assert int(m.group(4)) == 3                                      # the first sweep is dropped (messageQueue.h:67-72)
+        if gpus in (2, 8):
+            assert min(per_gpu) > 0 and max(per_gpu) - min(per_gpu) <= 3 * 12      # contiguous balanced step ranges
+        assert int(m.group(7)) == 8 * 12 // averaging                    # every spectrum of the last sweep is in the records
+
+
+def test_sweep_report_comes_from_the_merged_records(tool):
+    """The per-sweep report lines are built from the EXCHANGED records: per step, hits == the number of `freq` lines the
+    step printed in that sweep, whichever GPU processed it."""
+    r = subprocess.run([tool, "sweep", *sweep_args(3, 1, "peer", report=1)], capture_output=True, text=True, timeout=300, env=ENV)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = scan_lines(r.stdout)
+    sweeps, cur = [], None
+    for l in lines:
+        if l.startswith("Start scan"):
+            cur = {"hits": {}, "report": {}}
+            sweeps.append(cur)
+        elif l.startswith("freq "):
+            hz = int(l.split()[1])
+            step = min(range(8), key=lambda s: abs(2407.5e6 + 15e6 * s - hz))
+            cur["hits"][step] = cur["hits"].get(step, 0) + 1
+        elif l.startswith("sweep "):
+            f = l.split()
+            cur["report"][int(f[3])] = (int(f[7]), int(f[9]))
+    assert len(sweeps) == 3
+    for sw in sweeps:
+        assert sorted(sw["report"]) == list(range(8))
+        for step in range(8):
+            assert sw["report"][step] == (12, sw["hits"].get(step, 0)), (step, sw["report"][step], sw["hits"].get(step, 0))
 
 
 def test_hackrf_sweep_replay(tool, tmp_path):
@@ -239,5 +302,9 @@ def test_host_layer_is_clean_under_thread_sanitizer(tmp_path):
     r3 = subprocess.run([*prefix, tsan, "bench", "1", "2048", "8", "1", "64", "3000", "2", "256", "4", "64", "200"],
                         capture_output=True, text=True, timeout=600, env=ENV)
     assert r3.returncode == 0, r3.stderr[-2000:]
-    for r in (r1, r2, r3):
+    # SweepProcessor: router + 3 device workers + ordered emitter + sweep barrier
+    r4 = subprocess.run([*prefix, tsan, "sweep", *sweep_args(3, 2, "peer", report=1)], capture_output=True, text=True,
+                        timeout=600, env=ENV)
+    assert r4.returncode == 0, r4.stderr[-2000:]
+    for r in (r1, r2, r3, r4):
         assert "ThreadSanitizer" not in r.stderr and "ThreadSanitizer" not in r.stdout, (r.stderr + r.stdout)[-4000:]

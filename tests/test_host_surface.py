@@ -108,3 +108,40 @@ def test_hit_record_overflow_falls_back_to_full_list():
         want += [O.hit_frequency(case["freqs"][b], case["fs"], n, int(i)) for i in bins]
     got = [f for f, _ in GU.parse_hits(run_replay(case))]
     assert got == want
+
+
+# ---- SweepProcessor: one worker per GPU inside one process (csrc/host/sweepProcessor.cpp) -----------------------------
+SWEEP = ["1", "1024", "20000000", "8", "1", "17.0", "2400000000.0", "2520000000.0", "12", "4", "7"]   # 8 retune steps
+
+
+def _scan_lines(text):
+    return [re.sub(r"Start scan at .*", "Start scan at <wall clock>", l) for l in text.splitlines()
+            if not re.match(r"(Starting|Stopped) process thread|Starting source thread|Stopping source thread|"
+                            r"Frequency \d+:|Elapsed time", l)]
+
+
+def _run(args):
+    out = subprocess.run([TOOL, *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return out.stdout.decode(), out.stderr.decode()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_sweep_processor_equals_process_samples_on_every_gpu_count(exchange):
+    """`scan_b200 sweep` (SweepProcessor: steps split across GPUs, in-process ncclCommInitAll + ncclAllGather or the NVLink
+    peer-memory windows for the per-sweep records) prints exactly what `scan_b200 synth` (ProcessSamples, one worker)
+    prints, for 1 GPU and for every GPU count the box offers; the merged records account for the whole last sweep."""
+    import torch
+    want, err0 = _run(["synth", *SWEEP, "1", "1"])
+    want = _scan_lines(want)
+    assert sum(l.startswith("freq ") for l in want) > 100
+    hits = int(re.search(r"buffers (\d+) hits (\d+)", err0).group(2))
+    for gpus in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        got, err = _run(["sweep", *SWEEP, str(gpus), "1", exchange, "0"])
+        assert _scan_lines(got) == want, gpus
+        m = re.search(r"buffers (\d+) hits (\d+) launches (\d+) sweeps (\d+) per-gpu((?: \d+)+) last-sweep-records hits (\d+) "
+                      r"spectra (\d+)", err)
+        assert m and int(m.group(2)) == hits and int(m.group(4)) == 3 and int(m.group(7)) == 8 * 12
+        per_gpu = [int(x) for x in m.group(5).split()]
+        assert len(per_gpu) == gpus and min(per_gpu) > 0
