@@ -9,7 +9,7 @@ BUILD     := build
 LIB       := scanner_b200/libscanner_b200.so
 
 KOBJS := $(BUILD)/scn_k_byte.o $(BUILD)/scn_k_short.o $(BUILD)/scn_k_shortc.o $(BUILD)/scn_k_float.o
-OBJS  := $(BUILD)/scn_api.o $(BUILD)/scn_records.o $(BUILD)/scn_large.o $(BUILD)/scn_hackrf.o $(BUILD)/scn_convert.o $(BUILD)/scn_exchange.o $(BUILD)/scn_nccl.o $(KOBJS)
+OBJS  := $(BUILD)/scn_api.o $(BUILD)/scn_records.o $(BUILD)/scn_large.o $(BUILD)/scn_hackrf.o $(BUILD)/scn_convert.o $(BUILD)/scn_exchange.o $(BUILD)/scn_nccl.o $(BUILD)/scn_cluster.o $(KOBJS)
 HOSTSRC := $(wildcard $(CSRC)/host/*.cpp)
 HOSTOBJS := $(patsubst $(CSRC)/host/%.cpp,$(BUILD)/host_%.o,$(HOSTSRC))
 KHDRS := $(CSRC)/scn_fft.cuh $(CSRC)/scn_kernel.cuh $(CSRC)/scn_wpt.cuh $(CSRC)/scn_p64.cuh $(CSRC)/scn_wconst.cuh $(CSRC)/scn_dispatch.h $(CSRC)/scn_timedomain.cuh include/scanner_b200.h

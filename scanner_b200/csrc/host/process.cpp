@@ -30,7 +30,9 @@ ProcessSamples::ProcessSamples(uint32_t numSamples, uint32_t sampleRate, uint32_
   if (scn_window_build(windowType, numSamples, m_window.data()) != SCN_OK) Die("FFTWindow");
 }
 
-ProcessSamples::~ProcessSamples() {}
+ProcessSamples::~ProcessSamples() {
+  if (m_runCtx) scn_destroy(m_runCtx);
+}
 
 // Hit records per spectrum copied back with every batch; a spectrum with more hits than this is re-run
 // alone through a full-capacity context (rare: the reference itself treats > 1047 hits as an event,
@@ -302,7 +304,9 @@ void ProcessSamples::Run(int16_t sample_buffer[][2], uint32_t centerFrequency) {
   // Synchronous single-buffer path (process.cpp:131-144): convert -> window -> FFT -> detect on raw
   // int16 IQ.  (The reference's version dereferences a null header in process_fft and crashes;
   // here the centre frequency argument is used.)
-  scn_ctx* ctx = CreateContext(SampleQueue::ShortComplex, m_enob, false, 1, 0);
+  // the context (device tables, ticket slots) is created on the first call and kept: Run() is a per-buffer call
+  if (!m_runCtx) m_runCtx = CreateContext(SampleQueue::ShortComplex, m_enob, false, 1, 0);
+  scn_ctx* ctx = m_runCtx;
   std::vector<uint32_t> count(1);
   std::vector<scn_hit> hits(m_sampleCount);
   if (m_mode == FrequencyDomain) {
@@ -316,5 +320,4 @@ void ProcessSamples::Run(int16_t sample_buffer[][2], uint32_t centerFrequency) {
     m_hitCount += count[0];
   }
   m_launches++;
-  scn_destroy(ctx);
 }

@@ -92,6 +92,7 @@ class ProcessSamples {
   std::atomic<uint64_t> m_buffersProcessed{0}, m_hitCount{0}, m_launches{0};
   std::atomic<bool> m_writing{false};
   std::atomic<uint64_t> m_endSequenceId{0};
+  scn_ctx* m_runCtx = nullptr;                     // Run()'s context, created on first use
   bool m_zeroCopy = true;
   uint32_t m_minBatch = 0, m_lingerMicros = 0;
   std::atomic<uint64_t> m_zeroCopyBatches{0};

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -106,6 +107,7 @@ struct Slot {
   float* h_td = nullptr;
   uint32_t n_spectra = 0;
   bool busy = false;
+  bool ready = false;           // every buffer below was allocated (a half-built slot is freed, never used)
 };
 
 }  // namespace
@@ -125,6 +127,7 @@ struct scn_ctx {
   float2* d_twiddles = nullptr;
   scn::KernelVariant variant{};
   int ctas_per_sm = 1;
+  int max_clusters = 0;          // co-resident clusters (cluster variants only)
   int num_sms = 1;
   int regs = 0;
   // four-step path (N = 2^15, 2^16): N = 16 x N2
@@ -135,6 +138,7 @@ struct scn_ctx {
   float* d_p = nullptr;          // power [chunk spectra][16][N2]
   int2* d_dcs = nullptr;         // per-buffer dc
   uint32_t chunk_spectra = 0;
+  cudaEvent_t large_done = nullptr;   // the four-step scratch is per context: launches on different streams take turns
   // work counters of the persistent kernels (scn::WorkQueue): one per launch, rotated, self-resetting
   uint32_t* d_work = nullptr;
   uint32_t work_next = 0;
@@ -207,6 +211,10 @@ int launch_large(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d_spe
       c->chunk_spectra = want;
     }
   }
+  // d_y / d_p / d_dcs belong to the context, not to the stream: two tickets (or two user streams) in flight must
+  // not overwrite each other's intermediates, so every launch waits for the previous one's finalize kernel.
+  if (!c->large_done) SCN_CUDA(cudaEventCreateWithFlags(&c->large_done, cudaEventDisableTiming));
+  else SCN_CUDA(cudaStreamWaitEvent(stream, c->large_done, 0));
   for (uint32_t first = 0; first < n_spectra; first += c->chunk_spectra) {
     const uint32_t ns = (n_spectra - first < c->chunk_spectra) ? (n_spectra - first) : c->chunk_spectra;
     const uint32_t nb = ns * K;
@@ -228,6 +236,7 @@ int launch_large(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d_spe
                                   stream));
     c->launches++;
   }
+  SCN_CUDA(cudaEventRecord(c->large_done, stream));
   return SCN_OK;
 }
 
@@ -252,12 +261,30 @@ int launch_frequency(scn_ctx* c, const void* d_raw, uint32_t n_spectra, float* d
   p.dc_ignore = c->cfg.dc_ignore_window;
   p.win_mirror = c->win_mirror ? 1u : 0u;
   p.work = next_work_counter(c);
+  void* args[] = {&p};
+  if (c->variant.cluster > 0) {
+    // persistent clusters: as many as fit on the device, each walks spectra cluster_id, + n_clusters, ...
+    uint32_t n_clusters = uint32_t(c->max_clusters);
+    if (n_clusters > n_spectra) n_clusters = n_spectra;
+    if (n_clusters == 0) return SCN_OK;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(n_clusters * uint32_t(c->variant.cluster));
+    lc.blockDim = dim3(unsigned(c->variant.threads));
+    lc.dynamicSmemBytes = c->variant.smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = unsigned(c->variant.cluster); at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    lc.attrs = &at; lc.numAttrs = 1;
+    SCN_CUDA(cudaLaunchKernelExC(&lc, c->variant.func, args));
+    c->launches++;
+    return SCN_OK;
+  }
   const uint32_t F = uint32_t(c->variant.transforms_per_cta);
   const uint32_t n_groups = (n_spectra + F - 1) / F;
   uint32_t grid = uint32_t(c->ctas_per_sm) * uint32_t(c->num_sms);
   if (grid > n_groups) grid = n_groups;
   if (grid == 0) return SCN_OK;
-  void* args[] = {&p};
   SCN_CUDA(cudaLaunchKernel(c->variant.func, dim3(grid), dim3(c->variant.threads), args,
                             c->variant.smem_bytes, stream));
   c->launches++;
@@ -327,8 +354,15 @@ void free_slot(Slot& s) {
 }
 
 // Slot buffers are allocated on first use so device-resident-only callers pay nothing.
+int ensure_slot_alloc(scn_ctx* c, Slot& s);
 int ensure_slot(scn_ctx* c, Slot& s) {
-  if (s.stream) return SCN_OK;
+  if (s.ready) return SCN_OK;
+  const int rc = ensure_slot_alloc(c, s);
+  if (rc != SCN_OK) { free_slot(s); return rc; }     // e.g. out of memory half way: leave nothing half-initialised
+  s.ready = true;
+  return SCN_OK;
+}
+int ensure_slot_alloc(scn_ctx* c, Slot& s) {
   const size_t S = c->cfg.max_spectra;
   SCN_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   SCN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -439,9 +473,14 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
   auto bail = [&](int code) { scn_destroy(c); return code; };
 
   if (!td) {
-    c->large = log2n > scn::kMaxLog2N;
+    // N >= 2^14: one transform per thread-block cluster, single HBM pass (scn_cluster.cu).  SCN_FOUR_STEP=1 in the
+    // environment selects the older four-step path through an HBM intermediate (kept for A/B and as a cross-check).
+    const bool four_step = std::getenv("SCN_FOUR_STEP") != nullptr;
+    const bool clustered = log2n >= 14 && !four_step &&
+        scn::variant_cluster(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant);
+    c->large = !clustered && log2n > scn::kMaxLog2N;
     c->log2n2 = c->large ? log2n - 4 : log2n;
-    const bool found = c->large
+    const bool found = clustered ? true : c->large
         ? scn::variant_float_rows(c->log2n2, K > 1, &c->variant)
         : scn::find_variant(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant);
     if (!found)
@@ -457,6 +496,23 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
     if (e != cudaSuccess || occ < 1)
       return bail(fail(SCN_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e)));
     c->ctas_per_sm = occ;
+    if (c->variant.cluster > 0) {
+      // how many clusters can be co-resident (GPC boundaries may strand a few SMs): the persistent grid
+      c->ctas_per_sm = 1;
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3(unsigned(c->variant.cluster * c->num_sms));
+      lc.blockDim = dim3(unsigned(c->variant.threads));
+      lc.dynamicSmemBytes = c->variant.smem_bytes;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = unsigned(c->variant.cluster); at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      lc.attrs = &at; lc.numAttrs = 1;
+      int n_clusters = 0;
+      e = cudaOccupancyMaxActiveClusters(&n_clusters, c->variant.func, &lc);
+      if (e != cudaSuccess || n_clusters < 1)
+        return bail(fail(SCN_ERR_CUDA, "cluster occupancy query failed: %s", cudaGetErrorString(e)));
+      c->max_clusters = n_clusters;
+    }
     cudaFuncAttributes fa{};
     if (cudaFuncGetAttributes(&fa, c->variant.func) == cudaSuccess) c->regs = fa.numRegs;
 
@@ -485,6 +541,22 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
         for (int kk = 0; kk < 64; kk++) {
           const double a = -2.0 * kPi * double(kk + 64 * m) / 8192.0;
           tw[size_t(63 * 64) + size_t(m) * 64 + kk] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    }
+    if (c->variant.twiddle_layout == 3) {      // scn_cluster.cu: twA as above; twC[n1*64 + t] = W_N^(n1 t); twB[n1*64 + q] = W_N^(64 n1 q)
+      const int R = int(cf.sample_count / 4096);
+      tw.assign(size_t(63 * 64 + 2 * R * 64), make_float2(0.f, 0.f));
+      for (int r = 1; r < 64; r++)
+        for (int k = 0; k < 64; k++) {
+          const double a = -2.0 * kPi * double(k) * double(r) / 4096.0;
+          tw[size_t(r - 1) * 64 + k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+      for (int n1 = 0; n1 < R; n1++)
+        for (int x = 0; x < 64; x++) {
+          const double a = -2.0 * kPi * double(n1) * double(x) / double(cf.sample_count);
+          tw[size_t(63 * 64) + size_t(n1) * 64 + x] = make_float2(float(std::cos(a)), float(std::sin(a)));
+          const double b = -2.0 * kPi * 64.0 * double(n1) * double(x) / double(cf.sample_count);
+          tw[size_t(63 * 64 + R * 64) + size_t(n1) * 64 + x] = make_float2(float(std::cos(b)), float(std::sin(b)));
         }
     }
     if (c->variant.twiddle_layout == 1) {      // warp-per-transform kernel: exp(-2 pi i lane r / N), r = 1..63
@@ -536,6 +608,7 @@ SCN_API int scn_destroy(scn_ctx* c) {
   if (c->d_y) cudaFree(c->d_y);
   if (c->d_p) cudaFree(c->d_p);
   if (c->d_dcs) cudaFree(c->d_dcs);
+  if (c->large_done) cudaEventDestroy(c->large_done);
   if (c->d_conv_raw) cudaFree(c->d_conv_raw);
   if (c->d_conv_out) cudaFree(c->d_conv_out);
   delete c;
@@ -752,20 +825,28 @@ SCN_API int scn_process_host(scn_ctx* c, const void* raw, uint32_t n_spectra, fl
                        hits ? hits + size_t(pd.first) * c->hit_cap : nullptr,
                        td_max_min ? td_max_min + size_t(pd.first) * 2 : nullptr);
   };
+  // on any failure the tickets still in flight are collected (results discarded) so the context stays usable
+  auto drain = [&](int rc) {
+    const std::string msg = g_last_error;
+    for (const Pending& pd : inflight) scn_collect(c, pd.ticket, nullptr, nullptr, nullptr, nullptr, nullptr);
+    inflight.clear();
+    g_last_error = msg;
+    return rc;
+  };
   for (uint32_t first = 0; first < n_spectra; first += cap) {
     const uint32_t count = (n_spectra - first < cap) ? (n_spectra - first) : cap;
     if (inflight.size() == c->slots.size()) {
       int rc = collect_front();
-      if (rc != SCN_OK) return rc;
+      if (rc != SCN_OK) return drain(rc);
     }
     uint32_t ticket = 0;
     int rc = scn_submit(c, static_cast<const uint8_t*>(raw) + size_t(first) * chunk_bytes_per_spec, count, &ticket);
-    if (rc != SCN_OK) return rc;
+    if (rc != SCN_OK) return drain(rc);
     inflight.push_back({ticket, first, count});
   }
   while (!inflight.empty()) {
     int rc = collect_front();
-    if (rc != SCN_OK) return rc;
+    if (rc != SCN_OK) return drain(rc);
   }
   return SCN_OK;
 }

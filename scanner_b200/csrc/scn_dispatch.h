@@ -14,7 +14,8 @@ struct KernelVariant {
   size_t smem_bytes;
   int transforms_per_cta;
   const char* name;
-  int twiddle_layout;     // 0: pass tables of scn_fft.cuh; 1: warp-per-transform table [63][32] of scn_wpt.cuh; 2: scn_p64.cuh tables
+  int twiddle_layout;     // 0: pass tables of scn_fft.cuh; 1: warp-per-transform table [63][32] of scn_wpt.cuh; 2: scn_p64.cuh tables; 3: scn_cluster.cu
+  int cluster = 0;        // > 0: thread-block cluster of this many CTAs per transform (scn_cluster.cu), one CTA per SM
 };
 
 // One translation unit per sample kind (compiled in parallel); each fills its rows.
@@ -24,6 +25,8 @@ bool variant_short_complex(int log2n, bool dc, bool avg, KernelVariant* out);
 bool variant_float_complex(int log2n, bool dc, bool avg, KernelVariant* out);
 // row mode of the four-step path: fp32 complex rows of 2^11 / 2^12 points, power out
 bool variant_float_rows(int log2n, bool avg, KernelVariant* out);
+// N = 2^14 .. 2^16: one transform per cluster of 1 / 2 / 4 CTAs in distributed shared memory (scn_cluster.cu)
+bool variant_cluster(int kind, int log2n, bool dc, bool avg, KernelVariant* out);
 
 // avg: K > 1 (keeps the 16 accumulators live across the K loop; K == 1 kernels do not pay for them)
 inline bool find_variant(int kind, int log2n, bool dc, bool avg, KernelVariant* out) {

@@ -73,6 +73,7 @@ struct KernelParams {
   uint32_t win_mirror;
   // Work counter of this launch (WorkQueue below): [0] tiles handed out beyond the static ones, [1] takers retired.
   uint32_t* __restrict__ work;
+  uint32_t always_zero;                  // 0; see WorkQueue::take
 };
 
 // Dynamic tile distribution for the persistent kernels.  A "taker" (a warp in scn_wpt.cuh, a CTA elsewhere) owns
@@ -84,9 +85,21 @@ struct KernelParams {
 // between launches; a context rotates over several counters so launches on different streams never share one.
 struct WorkQueue {
   uint32_t* w;
-  uint32_t takers;
-  __device__ __forceinline__ WorkQueue(uint32_t* work, uint32_t n_takers) : w(work), takers(n_takers) {}
-  __device__ __forceinline__ uint32_t take() { return 2u * takers + atomicAdd(w, 1u); }
+  uint32_t takers, zero;
+  __device__ __forceinline__ WorkQueue(uint32_t* work, uint32_t n_takers, uint32_t always_zero)
+      : w(work), takers(n_takers), zero(always_zero) {}
+  // atomicAdd() on an address ptxas can prove warp-uniform is lowered to the warp-aggregated form (elect + ATOMG +
+  // SHFL of the result to the active lanes) -- also from inline PTX, also as atom.inc, also behind an empty asm --
+  // and that SHFL sits right behind the ATOMG: the warp then waits out the whole L2 round trip (10 % of all stall
+  // samples of the warp-per-transform kernel in ncu).  `zero` is a kernel parameter that is always 0: adding
+  // (zero & threadIdx.x) makes the address lane-dependent as far as ptxas can tell, so it emits a plain ATOMG whose
+  // result lands in a register nobody reads until the caller needs the index.
+#ifndef SCN_WQ_AGGREGATED
+#define SCN_WQ_AGGREGATED 0      // 1: the plain atomicAdd(w, 1) form, for A/B
+#endif
+  __device__ __forceinline__ uint32_t take() {
+    return 2u * takers + atomicAdd(w + (SCN_WQ_AGGREGATED ? 0u : (zero & threadIdx.x)), 1u);
+  }
   // called once per taker, after its last take() has returned
   __device__ __forceinline__ void retire() {
     if (atomicAdd(w + 1, 1u) == takers - 1u) { atomicExch(w, 0u); atomicExch(w + 1, 0u); }
@@ -362,8 +375,8 @@ spectrum_sense_kernel(const KernelParams p) {
 
   // ---- tile stream of this CTA: (group, k), k = 0..K-1; groups blockIdx.x and blockIdx.x + gridDim.x are
   // static, later ones come from the launch's work counter (WorkQueue above; row mode keeps the static stride) ----
-  WorkQueue wq(p.work, gridDim.x);
-  uint32_t g = blockIdx.x, g_after = blockIdx.x + gridDim.x, g_after2 = 0;
+  WorkQueue wq(p.work, gridDim.x, p.always_zero);
+  uint32_t g = blockIdx.x, g_after = blockIdx.x + gridDim.x, g_after2 = 0, ticket = 0;
   if (g >= n_groups) {
     if (!ROWS && tid == 0) wq.retire();
     return;
@@ -465,7 +478,8 @@ spectrum_sense_kernel(const KernelParams p) {
     if (nk == K) { nk = 0; ng = g_after; }
     const bool has_next = ng < n_groups;
     if constexpr (!ROWS) {
-      if (cur_k == 0 && tid == 0) swork[spar] = wq.take();   // the group after g_after; read behind the epilogue barrier
+      if (cur_k == 0 && tid == 0) ticket = wq.take();   // the group after g_after: requested now, parked in a register,
+                                                         // handed to the CTA behind the epilogue barrier
     }
     bool next_live = false;
     if (has_next) {
@@ -592,6 +606,7 @@ spectrum_sense_kernel(const KernelParams p) {
       if constexpr (kDC) {
         if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); }
       }
+      if (tid == 0) swork[spar] = ticket;
       __syncthreads();
       g_after2 = swork[spar];
       if constexpr (kDC) {

@@ -135,8 +135,8 @@ spectrum_sense_p64_kernel(const KernelParams p) {
 
   // ---- tile stream of this CTA: (spectrum, k), k = 0..K-1; spectra blockIdx.x and blockIdx.x + gridDim.x are
   // static, later ones come from the launch's work counter (WorkQueue, scn_kernel.cuh) ----
-  WorkQueue wq(p.work, gridDim.x);
-  uint32_t s = blockIdx.x, s_after = blockIdx.x + gridDim.x, s_after2 = 0, k = 0;
+  WorkQueue wq(p.work, gridDim.x, p.always_zero);
+  uint32_t s = blockIdx.x, s_after = blockIdx.x + gridDim.x, s_after2 = 0, k = 0, ticket = 0;
   if (s >= p.n_spectra) {
     if (t == 0) wq.retire();
     return;
@@ -209,7 +209,8 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     uint32_t ns = s, nk = k + 1;
     if (nk == K) { nk = 0; ns = s_after; }
     const bool has_next = ns < p.n_spectra;
-    if (k == 0 && t == 0) swork[spar] = wq.take();     // the spectrum after s_after; read behind the epilogue barrier
+    if (k == 0 && t == 0) ticket = wq.take();          // the spectrum after s_after: requested now, parked in a
+                                                       // register, handed to the CTA behind the epilogue barrier
     const bool epilogue_tile = (k == K - 1);
     const size_t buf_index = size_t(s) * K + k;
 
@@ -433,6 +434,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
           if (lane == 0) { sred[2 * G::WARPS * tpar + 2 * warp] = si; sred[2 * G::WARPS * tpar + 2 * warp + 1] = sq; }
         }
       }
+      if (t == 0) swork[spar] = ticket;
       __syncthreads();
       s_after2 = swork[spar];
       if constexpr (kDC) {

@@ -117,7 +117,7 @@ SWEEP = ["1", "1024", "20000000", "8", "1", "17.0", "2400000000.0", "2520000000.
 def _scan_lines(text):
     return [re.sub(r"Start scan at .*", "Start scan at <wall clock>", l) for l in text.splitlines()
             if not re.match(r"(Starting|Stopped) process thread|Starting source thread|Stopping source thread|"
-                            r"Frequency \d+:|Elapsed time", l)]
+                            r"Frequency \d+:|Elapsed time|NCCL version", l)]     # (NCCL announces itself on stdout)
 
 
 def _run(args):
