@@ -35,7 +35,9 @@ namespace scn {
 constexpr int kClM = 4096;                       // row length
 constexpr int kClRows = 4;                       // rows per CTA
 constexpr int kClThreads = 256;                  // 64 per row
-constexpr int kClRowElems = kClM + kClM / 64;    // padded row (one float2 per 64) for the in-place 64 x 64 exchange
+constexpr int kClRowElems = kClM + kClM / 64 + 4; // padded row (one float2 per 64) for the in-place 64 x 64 exchange, + 4
+                                                 // so that rows r and r + 2 sit 16 banks apart (phase-0 stores of a lane
+                                                 // pair go to rows {0,2} / {1,3} of the same column)
 constexpr int kClMaskWords = 512;                // mask words a CTA owns: R * (M/C/32) = 512 for every C
 
 struct ClusterSmem {
@@ -56,6 +58,8 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// arrive without the release fence: for barriers that only order earlier READS against later remote writes
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_shared(const void* p, uint32_t rank) {       // address of `p` in CTA `rank`'s smem
   uint32_t out;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
@@ -104,34 +108,32 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
   const float2* twB = twC + R * 64;
   float2* rows = sm.rows;
 
-  // ---- raw samples of one buffer, as loaded: this CTA's four rows are samples R n2 + 4 crank + {0..3}, n2 = tid + 256 u
-  // (4 consecutive samples per u: 32 B of fp32 IQ, 16 B of int16 IQ, 8 B of int8 IQ, 2 x 8 B of split int16).  They are
-  // loaded one buffer AHEAD, at the start of phase 2 (whose register need is small), so their HBM latency hides behind
-  // phase 2 and the epilogue; fp32 IQ with K > 1 has no registers to spare (64 accumulators) and loads in place.
-  constexpr int kRawWords = KIND == SCN_KIND_FLOAT_COMPLEX ? 8 : KIND == SCN_KIND_BYTE_COMPLEX ? 2 : 4;
-  constexpr bool kPrefetch = !(KIND == SCN_KIND_FLOAT_COMPLEX && AVG);
-  // fp32 IQ: 16 x 8 raw registers would spill next to phase 2's 96: half is loaded ahead, half in place
-  constexpr int kPre = !kPrefetch ? 0 : (KIND == SCN_KIND_FLOAT_COMPLEX ? 8 : 16);
-  uint32_t rawv[16][kRawWords];
+  // ---- raw samples of one buffer, as loaded.  This CTA's four rows are samples R n2 + 4 crank + {0..3}; a lane PAIR
+  // (tid even / odd) takes one n2 = tid / 2 + 128 u, u < 32: the even lane rows 0,1, the odd lane rows 2,3, so one warp-
+  // wide load covers 16 whole 32-byte groups (16 B per lane for fp32 IQ, 8 B for int16 IQ, 4 B for int8 IQ, 2 x 4 B for
+  // split int16) and every 128-byte line is touched once.  The loads are issued one buffer AHEAD, at the start of
+  // phase 2 (whose register need is small), so their HBM latency hides behind phase 2 and the epilogue; fp32 IQ keeps
+  // only half of them in registers that long (K > 1: none, 64 accumulators), the rest loads in place.
+  constexpr int kRawWords = KIND == SCN_KIND_FLOAT_COMPLEX ? 4 : KIND == SCN_KIND_BYTE_COMPLEX ? 1 : 2;
+  constexpr int kPre = KIND == SCN_KIND_FLOAT_COMPLEX ? (AVG ? 0 : 16) : 32;
+  const uint32_t lhalf = uint32_t(tid) & 1u, n2base = uint32_t(tid) >> 1;
+  uint32_t rawv[32][kRawWords];
   auto load_raw = [&](const uint8_t* buf, int u_begin, int u_end) {
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
+    for (int u = 0; u < 32; u++) {
       if (u < u_begin || u >= u_end) continue;
-      const size_t e = size_t(R) * (uint32_t(tid) + 256u * u) + 4u * crank;   // first of the 4 consecutive samples
+      const size_t e = size_t(R) * (n2base + 128u * u) + 4u * crank + 2u * lhalf;   // first of this lane's 2 samples
       if constexpr (KIND == SCN_KIND_FLOAT_COMPLEX) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(buf) + e / 2), b = __ldg(reinterpret_cast<const uint4*>(buf) + e / 2 + 1);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(buf) + e / 2);
         rawv[u][0] = a.x; rawv[u][1] = a.y; rawv[u][2] = a.z; rawv[u][3] = a.w;
-        rawv[u][4] = b.x; rawv[u][5] = b.y; rawv[u][6] = b.z; rawv[u][7] = b.w;
       } else if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(buf) + e / 4);
-        rawv[u][0] = v.x; rawv[u][1] = v.y;
+        rawv[u][0] = __ldg(reinterpret_cast<const uint32_t*>(buf) + e / 2);
       } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf) + e / 4);
-        rawv[u][0] = v.x; rawv[u][1] = v.y; rawv[u][2] = v.z; rawv[u][3] = v.w;
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(buf) + e / 2);
+        rawv[u][0] = v.x; rawv[u][1] = v.y;
       } else {                                                               // split: I block, then Q block
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(buf) + e / 4);
-        const uint2 b = __ldg(reinterpret_cast<const uint2*>(buf + size_t(N) * 2) + e / 4);
-        rawv[u][0] = a.x; rawv[u][1] = a.y; rawv[u][2] = b.x; rawv[u][3] = b.y;
+        rawv[u][0] = __ldg(reinterpret_cast<const uint32_t*>(buf) + e / 2);
+        rawv[u][1] = __ldg(reinterpret_cast<const uint32_t*>(buf + size_t(N) * 2) + e / 2);
       }
     }
   };
@@ -139,25 +141,28 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
   auto raw_sums = [&](int& si, int& sq) {
     si = 0; sq = 0;
 #pragma unroll
-    for (int u = 0; u < 16; u++)
+    for (int u = 0; u < 32; u++) {
+      if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) {
+        si = __dp4a(int(rawv[u][0]), 0x00010001, si); sq = __dp4a(int(rawv[u][0]), 0x01000100, sq);
+      } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
 #pragma unroll
-      for (int x = 0; x < kRawWords; x++) {
-        const int wv = int(rawv[u][x]);
-        if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) { si = __dp4a(wv, 0x00010001, si); sq = __dp4a(wv, 0x01000100, sq); }
-        else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) { si = __dp2a_lo(wv, 0x00000001, si); sq = __dp2a_lo(wv, 0x00000100, sq); }
-        else if constexpr (KIND == SCN_KIND_SHORT) { if (x < 2) si = __dp2a_lo(wv, 0x00000101, si); else sq = __dp2a_lo(wv, 0x00000101, sq); }
+        for (int x = 0; x < 2; x++) { si = __dp2a_lo(int(rawv[u][x]), 0x00000001, si); sq = __dp2a_lo(int(rawv[u][x]), 0x00000100, sq); }
+      } else if constexpr (KIND == SCN_KIND_SHORT) {
+        si = __dp2a_lo(int(rawv[u][0]), 0x00000101, si); sq = __dp2a_lo(int(rawv[u][1]), 0x00000101, sq);
       }
+    }
   };
-  // convert + scale + window (utility.cpp:27-30,52-55,80-83; process.cpp:28-34) into the four rows
+  // convert + scale + window (utility.cpp:27-30,52-55,80-83; process.cpp:28-34) into rows 2 lhalf and 2 lhalf + 1
   auto store_rows = [&](int dci, int dcq) {
-    const float4* win = reinterpret_cast<const float4*>(p.window);
+    const float2* win = reinterpret_cast<const float2*>(p.window);
+    float2* r0 = rows + (2u * lhalf) * kClRowElems;
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const uint32_t n2 = uint32_t(tid) + 256u * u;
-      const float4 w = __ldg(win + (size_t(R) * n2 + 4u * crank) / 4);       // taps pre-scaled by 1/max (exact)
-      const float ws[4] = {w.x, w.y, w.z, w.w};
+    for (int u = 0; u < 32; u++) {
+      const uint32_t n2 = n2base + 128u * u;
+      const float2 w = __ldg(win + (size_t(R) * n2 + 4u * crank + 2u * lhalf) / 2);   // taps pre-scaled by 1/max (exact)
+      const float ws[2] = {w.x, w.y};
 #pragma unroll
-      for (int x = 0; x < 4; x++) {
+      for (int x = 0; x < 2; x++) {
         float2 val;
         if constexpr (KIND == SCN_KIND_FLOAT_COMPLEX) {
           val = __fmul2_rn(make_float2(__uint_as_float(rawv[u][2 * x]), __uint_as_float(rawv[u][2 * x + 1])),
@@ -165,19 +170,19 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
         } else {
           int xi, xq;
           if constexpr (KIND == SCN_KIND_BYTE_COMPLEX) {
-            const uint32_t h = rawv[u][x >> 1] >> (16 * (x & 1));
+            const uint32_t h = rawv[u][0] >> (16 * x);
             xi = int(static_cast<signed char>(h & 0xff));
             xq = int(static_cast<signed char>((h >> 8) & 0xff));
           } else if constexpr (KIND == SCN_KIND_SHORT_COMPLEX) {
             xi = int(static_cast<short>(rawv[u][x] & 0xffff));
             xq = int(static_cast<short>(rawv[u][x] >> 16));
           } else {
-            xi = int(static_cast<short>((rawv[u][x >> 1] >> (16 * (x & 1))) & 0xffff));
-            xq = int(static_cast<short>((rawv[u][2 + (x >> 1)] >> (16 * (x & 1))) & 0xffff));
+            xi = int(static_cast<short>((rawv[u][0] >> (16 * x)) & 0xffff));
+            xq = int(static_cast<short>((rawv[u][1] >> (16 * x)) & 0xffff));
           }
           val = make_float2(__fmul_rn(float(xi - dci), ws[x]), __fmul_rn(float(xq - dcq), ws[x]));
         }
-        rows[x * kClRowElems + n2] = val;
+        r0[x * kClRowElems + n2] = val;
       }
     }
   };
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
   for (uint32_t s = cluster_id; s < p.n_spectra; s += n_clusters) {
     for (uint32_t k = 0; k < K; k++) {
       // ---- phase 0: [DC], convert + window into this CTA's four rows -------------------------------------------------
-      if constexpr (kPre < 16) load_raw(buffer_ptr(s, k), kPre, 16);
+      if constexpr (kPre < 32) load_raw(buffer_ptr(s, k), kPre, 32);
       int dci = 0, dcq = 0;
       if constexpr (kDC) {
         int si, sq;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < 64; r++) v[r] = row[t + 65 * r];
-      if constexpr (C > 1) cluster_arrive();             // this CTA is done reading its rows (wait: before the exchange)
+      if constexpr (C > 1) cluster_arrive_relaxed();     // this CTA is done reading its rows (wait: before the exchange)
       {
         // v[8a + b] *= W_N^(n1 t) * W_4096^(t (8a + b)); the thread constant rides on the w^(8a) factors
         const float2* tw = twA + t;
@@ -265,15 +270,23 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
       else __syncthreads();
       {
         const float2* tb = twB + n1 * 64;
-        uint32_t dst[C];
+        float2* own = rows + size_t(n1) * KL + t;        // S[n1][t + 64 (q mod QPC)] of whichever CTA owns q
+        constexpr int QPC = 64 / C;                      // q values per owner
 #pragma unroll
-        for (int c = 0; c < C; c++) dst[c] = map_shared(rows + size_t(n1) * KL + t, uint32_t(c));
+        for (int c = 0; c < C; c++) {
+          if (uint32_t(c) == crank) {                    // this CTA's own share: plain shared-memory stores
 #pragma unroll
-        for (int x = 0; x < 64; x++) {
-          constexpr int QPC = 64 / C;                    // q values per owner
-          const int q = dft64_out_index(x);
-          const float2 val = cmul(v[x], __ldg(tb + q));  // times W_N^(64 n1 q)
-          st_cluster(dst[q / QPC] + uint32_t(sizeof(float2)) * 64u * uint32_t(q % QPC), val);
+            for (int x = 0; x < 64; x++)
+              if (dft64_out_index(x) / QPC == c)
+                own[64 * (dft64_out_index(x) % QPC)] = cmul(v[x], __ldg(tb + dft64_out_index(x)));   // times W_N^(64 n1 q)
+          } else {
+            const uint32_t dst = map_shared(own, uint32_t(c));
+#pragma unroll
+            for (int x = 0; x < 64; x++)
+              if (dft64_out_index(x) / QPC == c)
+                st_cluster(dst + uint32_t(sizeof(float2)) * 64u * uint32_t(dft64_out_index(x) % QPC),
+                           cmul(v[x], __ldg(tb + dft64_out_index(x))));
+          }
         }
       }
       cluster_arrive();

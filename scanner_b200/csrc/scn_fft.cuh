@@ -25,60 +25,15 @@
 
 namespace scn {
 
-// Raw IQ is read exactly once.  SCN_STREAM_LOADS=1 loads it through the read-only path WITHOUT allocating in L1
-// (ld.global.nc.L1::no_allocate), meant to keep the streaming data from evicting the window / twiddle tables.
-// Measured on B200 (tools/kbench.py A/B): no gain for the 1- and 2-byte kinds and 3 % SLOWER for fp32 IQ at
-// N = 4096 / 8192, so the default stays the plain __ldg path; what fixed the table misses at N = 8192 was
-// halving the table footprint (scn_p64.cuh).
-#ifndef SCN_STREAM_LOADS
-#define SCN_STREAM_LOADS 0
-#endif
-__device__ __forceinline__ unsigned short ldg_stream(const unsigned short* p) {
-#if SCN_STREAM_LOADS
-  unsigned short v;
-  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
-__device__ __forceinline__ unsigned int ldg_stream(const unsigned int* p) {
-#if SCN_STREAM_LOADS
-  unsigned int v;
-  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
-__device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
-#if SCN_STREAM_LOADS
-  uint2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-#if SCN_STREAM_LOADS
-  uint4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
-__device__ __forceinline__ float2 ldg_stream(const float2* p) {
-#if SCN_STREAM_LOADS
-  float2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
+// Raw IQ is read exactly once, through the read-only path.  (Loading it WITHOUT allocating in L1 --
+// ld.global.nc.L1::no_allocate, to keep the stream from evicting the window / twiddle tables -- was measured on B200:
+// no gain for the 1- and 2-byte kinds, 3 % slower for fp32 IQ at N = 4096 / 8192; removed.  What fixed the table
+// misses there was halving the table footprint and, later, landing the raw stream by TMA: scn_p64.cuh.)
+__device__ __forceinline__ unsigned short ldg_stream(const unsigned short* p) { return __ldg(p); }
+__device__ __forceinline__ unsigned int ldg_stream(const unsigned int* p) { return __ldg(p); }
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ldg_stream(const float2* p) { return __ldg(p); }
 
 constexpr int kPts = 16;   // complex points per thread
 
@@ -236,14 +191,6 @@ __device__ __forceinline__ void pass_gather(float2 (&v)[kPts], const float2* __r
   const float2* base = xch + xpad(t);
 #pragma unroll
   for (int q = 0; q < kPts; q++) v[q] = base[q * (T + T / 16)];
-}
-
-// Twiddle factors of pass P >= 1 for thread t: tw[((P-1)*15 + r-1)*T + t], r = 1..15.
-template <int LOG2N, int P>
-__device__ __forceinline__ void load_twiddles(float2 (&w)[15], const float2* __restrict__ tw, int t) {
-  constexpr int T = (1 << LOG2N) / 16;
-#pragma unroll
-  for (int r = 1; r < 16; r++) w[r - 1] = __ldg(&tw[((P - 1) * 15 + (r - 1)) * T + t]);
 }
 
 // Same 15 factors from the first one by a depth-4 product tree (w^2, w^4, w^8, then products):

@@ -23,18 +23,13 @@
 #include "scn_fft.cuh"
 #include "../../include/scanner_b200.h"
 
-// Twiddle strategy (tuning knobs):
-//   SCN_TWMODE 0: every twiddle is an L1-resident LDG per tile
-//              1: the LAST pass's 15 factors live in registers for the whole launch
-//              2: all passes' factors live in registers
-//              3: one LDG per pass + a 14-multiply product tree per tile
-//              5: six LDGs (w^1..4, w^8, w^12) + nine single products per pass (one rounding deep)
-//              6: LDG for the first twiddled pass (few distinct values per warp), mode 5 for the rest
-//              4: product tree for the LAST pass only (its 15 factors are all distinct per thread);
-//                 earlier passes (few distinct values per warp, L1 broadcast) stay LDG
-#ifndef SCN_TWMODE
-#define SCN_TWMODE 5     // measured on B200 (profiles/README.md): within 1 % of the fastest mode (3) at N <= 4096
-#endif                   // and as accurate as plain table loads (mode 3's squarings cost 1.5x in rms error)
+// Twiddle strategy of a radix-16 pass (15 factors per thread).  Two schemes survived the A/B runs on B200
+// (profiles/README.md; plain table loads, factors hoisted into registers for the whole launch, and mixed schemes were
+// measured and removed):
+//   kTwProducts: six loads (w^1..4, w^8, w^12) + nine single products -- one rounding deep, as accurate as 15 table
+//                loads and 4 % faster because the L1 pipe is a co-bottleneck; every size below 2^14
+//   kTwTree:     one load + a 14-multiply product tree (1.5x the rms error); N = 2^14 only, whose 1024-thread CTAs
+//                run at 64 registers and spill with anything wider (+10-13 %)
 // Other knobs used to explore the occupancy / register trade (defaults = measured best):
 #ifndef SCN_XBUFS_MAXLOG2
 #define SCN_XBUFS_MAXLOG2 13   // ping-pong exchange tiles up to this size, single tile (two barriers) above
@@ -42,9 +37,6 @@
 #ifndef SCN_WINREG_MAXLOG2
 #define SCN_WINREG_MAXLOG2 13  // window taps live in registers up to this size, L1 loads per tile above
 #endif
-#ifndef SCN_TWMODE_BIG
-#define SCN_TWMODE_BIG 3       // N = 2^14 runs 1024-thread CTAs at 64 registers: the power tree's 1 load per pass
-#endif                         // and no window registers spill least (measured +10-13 %, profiles/README.md)
 
 namespace scn {
 
@@ -94,12 +86,8 @@ struct WorkQueue {
   // samples of the warp-per-transform kernel in ncu).  `zero` is a kernel parameter that is always 0: adding
   // (zero & threadIdx.x) makes the address lane-dependent as far as ptxas can tell, so it emits a plain ATOMG whose
   // result lands in a register nobody reads until the caller needs the index.
-#ifndef SCN_WQ_AGGREGATED
-#define SCN_WQ_AGGREGATED 0      // 1: the plain atomicAdd(w, 1) form, for A/B
-#endif
-  __device__ __forceinline__ uint32_t take() {
-    return 2u * takers + atomicAdd(w + (SCN_WQ_AGGREGATED ? 0u : (zero & threadIdx.x)), 1u);
-  }
+  // (Kernel time did not move in the A/B -- the other warp of the scheduler filled the gap -- but the stall is gone.)
+  __device__ __forceinline__ uint32_t take() { return 2u * takers + atomicAdd(w + (zero & threadIdx.x), 1u); }
   // called once per taker, after its last take() has returned
   __device__ __forceinline__ void retire() {
     if (atomicAdd(w + 1, 1u) == takers - 1u) { atomicExch(w, 0u); atomicExch(w + 1, 0u); }
@@ -428,27 +416,12 @@ spectrum_sense_kernel(const KernelParams p) {
     odcq = int(unsigned(sq) >> LOG2N);
   };
 
-  // twiddles kept in registers for the whole launch (mode 1 / 2)
-  constexpr int kTw = (LOG2N >= 14) ? SCN_TWMODE_BIG : SCN_TWMODE;
-  constexpr bool kHoist1 = (kTw == 2) || (kTw == 1 && NP == 2);
-  constexpr bool kHoist2 = (kTw == 2) || (kTw == 1 && NP == 3);
-  constexpr bool kHoist3 = (kTw == 2) || (kTw == 1 && NP == 4);
-  float2 twr1[15], twr2[15], twr3[15];
-  if constexpr (kHoist1) load_twiddles<LOG2N, 1>(twr1, p.twiddles, t);
-  if constexpr (kHoist2 && NP > 2) load_twiddles<LOG2N, 2>(twr2, p.twiddles, t);
-  if constexpr (kHoist3 && NP > 3) load_twiddles<LOG2N, 3>(twr3, p.twiddles, t);
+  constexpr bool kTwTree = LOG2N >= 14;
 // The twiddles of pass P do not depend on the exchange that feeds it, so they are produced BEFORE
 // the scatter/barrier (their loads and products overlap the barrier wait) and applied after the gather.
-#define SCN_TWIDDLE_PREP(P, HOISTED, TWL)                                                \
-    if constexpr (!(HOISTED)) {                                                          \
-      if constexpr (kTw == 3 || (kTw == 4 && (P) == NP - 1))                             \
-        power_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                    \
-      else if constexpr (kTw == 5 || (kTw == 6 && (P) > 1))                              \
-        product_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
-      else load_twiddles<LOG2N, P>(TWL, p.twiddles, t);                                  \
-    }
-#define SCN_TWIDDLE_APPLY(HOISTED, REGS, TWL)                                            \
-    if constexpr (HOISTED) { apply_twiddles(v, REGS); } else { apply_twiddles(v, TWL); }
+#define SCN_TWIDDLE_PREP(P, TWL)                                                         \
+    if constexpr (kTwTree) power_twiddles<LOG2N, P>(TWL, p.twiddles, t);                 \
+    else product_twiddles<LOG2N, P>(TWL, p.twiddles, t);
 
   Raw raw;
   int dci = 0, dcq = 0;
@@ -515,23 +488,23 @@ spectrum_sense_kernel(const KernelParams p) {
     }
     {
       float2 twl[15];
-      SCN_TWIDDLE_PREP(1, kHoist1, twl)
+      SCN_TWIDDLE_PREP(1, twl)
       SCN_EXCHANGE(0, NP == 2)
-      SCN_TWIDDLE_APPLY(kHoist1, twr1, twl)
+      apply_twiddles(v, twl);
       dft16(v);
     }
     if constexpr (NP > 2) {
       float2 twl[15];
-      SCN_TWIDDLE_PREP(2, kHoist2, twl)
+      SCN_TWIDDLE_PREP(2, twl)
       SCN_EXCHANGE(1, NP == 3)
-      SCN_TWIDDLE_APPLY(kHoist2, twr2, twl)
+      apply_twiddles(v, twl);
       dft16(v);
     }
     if constexpr (NP > 3) {
       float2 twl[15];
-      SCN_TWIDDLE_PREP(3, kHoist3, twl)
+      SCN_TWIDDLE_PREP(3, twl)
       SCN_EXCHANGE(2, NP == 4)
-      SCN_TWIDDLE_APPLY(kHoist3, twr3, twl)
+      apply_twiddles(v, twl);
       dft16(v);
     }
 #undef SCN_EXCHANGE
@@ -668,7 +641,6 @@ spectrum_sense_kernel(const KernelParams p) {
   }
   if (!ROWS && tid == 0) wq.retire();
 #undef SCN_TWIDDLE_PREP
-#undef SCN_TWIDDLE_APPLY
 }
 
 }  // namespace scn

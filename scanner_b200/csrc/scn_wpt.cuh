@@ -131,12 +131,7 @@ __host__ __device__ constexpr int dft64_out_index(int slot) { return (slot >> 3)
 #ifndef SCN_WPT_MINCTAS
 #define SCN_WPT_MINCTAS 4
 #endif
-#ifndef SCN_WPT_TWLOAD
-#define SCN_WPT_TWLOAD 0
-#endif
-#ifndef SCN_WPT_LATESHFL
-#define SCN_WPT_LATESHFL 1
-#endif
+
 template <bool DC>
 __global__ void __launch_bounds__(32 * kWptWarpsPerCta, SCN_WPT_MINCTAS)
 spectrum_sense_wpt_kernel(const KernelParams p) {
@@ -220,11 +215,7 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     for (int r = 0; r < 64; r++) v[r] = tile[lane + 32 * r + (r >> 1)];
     {
       const float2* tw = p.twiddles + lane;
-#if SCN_WPT_TWLOAD
-      // all 63 factors from the (L1-resident, 16 KB) table: 49 more loads, 49 fewer complex products
-#pragma unroll
-      for (int r = 1; r < 64; r++) v[r] = cmul(v[r], __ldg(tw + (r - 1) * 32));
-#else
+      // 14 table values + 49 single products; all 63 from the (L1-resident, 16 KB) table measured 0.6 % slower
       float2 wb[8];                                // w^1 .. w^7
 #pragma unroll
       for (int b = 1; b < 8; b++) { wb[b] = __ldg(tw + (b - 1) * 32); v[b] = cmul(v[b], wb[b]); }
@@ -235,7 +226,6 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
 #pragma unroll
         for (int b = 1; b < 8; b++) v[8 * a + b] = cmul(v[8 * a + b], cmul(wa, wb[b]));
       }
-#endif
     }
     dft64_inplace(v);
 
@@ -313,11 +303,8 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
 
     if (!has_next) break;
     s_cur = s_next;
-#if SCN_WPT_LATESHFL
-    // Keep the broadcast of the ticket HERE, behind the epilogue's stores: left to itself ptxas hoists the SHFL to
-    // right after the ATOMG, and the warp then sits out the whole L2 round trip (10 % of all stall samples in ncu).
+    // keep the broadcast of the ticket HERE, behind the epilogue's stores (see WorkQueue::take)
     asm volatile("" : "+r"(ticket) : : "memory");
-#endif
     s_next = __shfl_sync(0xffffffffu, ticket, 0);
   }
   if (lane == 0) wq.retire();

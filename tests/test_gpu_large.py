@@ -1,5 +1,8 @@
-"""GPU: N = 2^15 and 2^16 (four-step path through an HBM intermediate, scn_large.cu) against the oracle:
-same contract as the in-CTA sizes -- masks / counts / hit order bit-exact, power within 1e-3 dB."""
+"""GPU: N = 2^15 and 2^16 against the oracle, same contract as the in-CTA sizes -- masks / counts / hit order bit-exact,
+power within 1e-3 dB -- through BOTH large-N paths: the default single-pass cluster kernel (scn_cluster.cu: one transform
+per 2- / 4-CTA cluster in distributed shared memory) and the older four-step path through an HBM intermediate
+(scn_large.cu, SCN_FOUR_STEP=1), which also serves as an independent cross-check of the cluster kernel."""
+import os
 import numpy as np
 import pytest
 
@@ -15,6 +18,34 @@ pytestmark = pytest.mark.gpu
 def test_large_parity(log2n, kind, enob, dc):
     # one more twiddle stage (W_N in fp32) than the in-CTA path: rms error class 4x the CPU fp32 FFT
     run_case(kind, 1 << log2n, enob, dc, 1, 3, seed=700 + log2n * 10 + kind, acc_factor=4.0)
+
+
+@pytest.fixture
+def four_step(monkeypatch):
+    monkeypatch.setenv("SCN_FOUR_STEP", "1")        # read by scn_create
+
+
+@pytest.mark.parametrize("log2n,kind,enob,dc", [(15, S.KIND_BYTE_COMPLEX, 8, True), (16, S.KIND_FLOAT_COMPLEX, 0, False),
+                                                (16, S.KIND_SHORT_COMPLEX, 12, True)])
+def test_four_step_path_parity(four_step, log2n, kind, enob, dc):
+    run_case(kind, 1 << log2n, enob, dc, 1, 3, seed=700 + log2n * 10 + kind, acc_factor=4.0)
+
+
+def test_four_step_two_tickets_in_flight_do_not_share_scratch(four_step):
+    # chunked submits keep two tickets in flight on different streams; the per-context intermediates are serialised
+    run_case(S.KIND_SHORT_COMPLEX, 1 << 15, 12, True, 2, 7, seed=811, max_spectra=2, hit_cap=5, acc_factor=4.0)
+
+
+def test_cluster_kernel_is_the_default_large_path():
+    w = S.window_build(S.WIN_HANN, 1 << 16)
+    with S.SpectrumSense(1 << 16, 8_000_000, 0, 10.0, w, sample_kind=S.KIND_FLOAT_COMPLEX, max_spectra=1) as ss:
+        assert "cluster" in ss.kernel_name and "DSMEM" in ss.kernel_name
+
+
+@pytest.mark.parametrize("kind,enob,dc,K", [(S.KIND_FLOAT_COMPLEX, 0, False, 1), (S.KIND_SHORT_COMPLEX, 12, True, 3),
+                                            (S.KIND_SHORT, 12, False, 1)])
+def test_cluster_kernel_single_cta_size(kind, enob, dc, K):
+    run_case(kind, 1 << 14, enob, dc, K, 5, seed=640 + kind, acc_factor=4.0)        # C = 1: 4 rows x 4096 in one CTA
 
 
 def test_large_averaging_and_chunking():
