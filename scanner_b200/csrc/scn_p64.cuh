@@ -105,12 +105,14 @@ spectrum_sense_p64_kernel(const KernelParams p) {
   // column parity hi = t / 64): slots 0..31 hold X[kk + 64 (m + 32 hi)], slots 32..63 the same + 4096.
   // Either way the lanes of a warp hold 32 CONSECUTIVE bins in a slot, i.e. exactly one mask word.
   const uint32_t bin_base = LOG2N == 13 ? uint32_t(t & 63) + 2048u * uint32_t(t >> 6) : uint32_t(t);
-  auto bin_of = [&](int x) -> uint32_t {
-    return LOG2N == 13 ? bin_base + 64u * uint32_t(x & 31) + 4096u * uint32_t(x >> 5)
-                       : bin_base + uint32_t(T) * uint32_t(dft64_out_index(x));
+  // bin of slot x relative to bin_base (a compile-time constant for a compile-time x)
+  auto bin_rel = [](int x) -> uint32_t {
+    return LOG2N == 13 ? 64u * uint32_t(x & 31) + 4096u * uint32_t(x >> 5) : uint32_t(T) * uint32_t(dft64_out_index(x));
   };
-  // mask word (shifted index >> 5) of slot x for this warp
-  auto word_of = [&](int x) -> uint32_t { return ((bin_of(x) - uint32_t(lane)) ^ half) >> 5; };
+  auto bin_of = [&](int x) -> uint32_t { return bin_base + bin_rel(x); };
+  // mask word (shifted index >> 5) of slot x for this warp: lane 0's bin is bin_base - lane
+  const uint32_t word_base = (bin_base - uint32_t(lane)) >> 5;
+  auto word_of = [&](int x) -> uint32_t { return (word_base + (bin_rel(x) >> 5)) ^ (half >> 5); };
 
   // int32 sums of I and Q over the staged buffer (utility.cpp:44-48): this thread's words t + T i
   auto staged_sums = [&](int& si, int& sq) {
@@ -387,14 +389,14 @@ spectrum_sense_p64_kernel(const KernelParams p) {
     } else {
       // ---- dB, spectrum out, detection (slot x <-> FFT bin bin_of(x)) ----------------------------------------------
       uint32_t* sm = smask + spar * G::WORDS;
-      float* out = p.spectra ? p.spectra + size_t(s) * N : nullptr;
+      float* out = p.spectra ? p.spectra + size_t(s) * N + bin_base : nullptr;
       bool anyraw = false;
 #pragma unroll
       for (int x = 0; x < 64; x++) {
         const float pbar = AVG ? __fmul_rn(v[x].x, p.inv_averaging) : v[x].x;
         const float db = kDbPerLog2 * __log2f(pbar);
         v[x].x = db;
-        if (out) out[bin_of(x)] = db;
+        if (out) out[bin_rel(x)] = db;
         anyraw = anyraw || (db > p.threshold);          // strict >, NaN never hits (process.cpp:54)
       }
       // this warp owns mask words word_of(x), x = 0..63: zero them (two per lane), then fill on demand
