@@ -500,10 +500,8 @@ def main() -> None:
                                 units_per_step, n_steps, d_recs[par].data_ptr(), side.cuda_stream)
             out_free[par].record(side)
             if xch is not None:
-                seq = xch.publish(d_recs[par].data_ptr(), side.cuda_stream)
-                if seq > 1:
-                    xch.merge(seq - 1, d_merged.data_ptr(), side.cuda_stream)   # the previous batch: its rows landed long ago
-                last_seq[0] = seq
+                # publish(i) + merge(i - 1) in one launch: the previous batch's rows landed long ago
+                last_seq[0] = xch.step(d_recs[par].data_ptr(), d_merged.data_ptr(), side.cuda_stream)
             elif world > 1:
                 S.gather_step_records(d_recs[par], world, out=d_gathers[par])   # NCCL all-gather, ~13 KB per rank
                 ctx.merge_step_records(d_gathers[par].data_ptr(), world, n_steps, d_merged.data_ptr(),
@@ -562,8 +560,10 @@ def main() -> None:
     launches0 = ctx.launch_count
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(stream)
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         step(True)
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps      # CPU time to enqueue one step (no sync inside)
     drain()
     t1.record(stream)
     barrier()
@@ -795,6 +795,7 @@ def main() -> None:
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_2_threads": cpu2, "cpu_fft_only_upper_bound": cpu_fft,
             "parity": parity, "records_check": records_check, "step_ms": step_ms,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "per_config": per_config, "sustained": sustained, "plugin_e2e": plugin,
         }
         print(json.dumps(line), flush=True)

@@ -219,6 +219,10 @@ SCN_API int scn_exchange_connect_ipc(scn_exchange* x, const unsigned char* handl
 SCN_API int scn_exchange_connect_local(scn_exchange* const* all /* [world], index == rank */, uint32_t world);
 SCN_API int scn_exchange_publish(scn_exchange* x, const uint32_t* d_records, void* stream, uint64_t* seq_out);
 SCN_API int scn_exchange_merge(scn_exchange* x, uint64_t seq, uint32_t* d_merged, void* stream);
+/* publish(d_records) and merge(previous sequence number) in ONE kernel launch -- the steady-state call of a batch loop
+ * (the first call merges nothing; after the last batch one scn_exchange_merge(last seq) closes the loop). */
+SCN_API int scn_exchange_step(scn_exchange* x, const uint32_t* d_records, uint32_t* d_merged_previous, void* stream,
+                              uint64_t* seq_out);
 /* host-pointer forms (synchronous): upload + publish; wait + merge + download */
 SCN_API int scn_exchange_publish_host(scn_exchange* x, const uint32_t* host_records, uint64_t* seq_out);
 SCN_API int scn_exchange_merge_host(scn_exchange* x, uint64_t seq, uint32_t* host_merged);

@@ -80,6 +80,7 @@ SYMBOLS = [
     ("scn_exchange_connect_local", _I, [C.POINTER(_VP), _U32]),
     ("scn_exchange_publish", _I, [_VP, _VP, _VP, C.POINTER(_U64)]),
     ("scn_exchange_merge", _I, [_VP, _U64, _VP, _VP]),
+    ("scn_exchange_step", _I, [_VP, _VP, _VP, _VP, C.POINTER(_U64)]),
     ("scn_exchange_publish_host", _I, [_VP, _VP, C.POINTER(_U64)]),
     ("scn_exchange_merge_host", _I, [_VP, _U64, _VP]),
     ("scn_nccl_gather_create", _I, [C.POINTER(_I), _U32, _U32, _U32, C.POINTER(_VP)]),
@@ -357,6 +358,12 @@ class RecordExchange:
     def publish(self, d_records: int, stream: int = 0) -> int:
         seq = _U64(0)
         _check(self._lib.scn_exchange_publish(self._x, _VP(d_records), _VP(stream or None), C.byref(seq)))
+        return int(seq.value)
+
+    def step(self, d_records: int, d_merged_previous: int, stream: int = 0) -> int:
+        """publish(d_records) + merge(previous batch) in one launch; returns this batch's sequence number."""
+        seq = _U64(0)
+        _check(self._lib.scn_exchange_step(self._x, _VP(d_records), _VP(d_merged_previous), _VP(stream or None), C.byref(seq)))
         return int(seq.value)
 
     def merge(self, seq: int, d_merged: int, stream: int = 0) -> None:

@@ -75,9 +75,9 @@ publish_records_kernel(const uint32_t* __restrict__ records, uint32_t* const* __
   uint32_t* win = peers[blockIdx.x];
   uint32_t* dst = win + data_offset(slot, rank, world, rec_total);
   for (uint32_t x = threadIdx.x; x < rec_total; x += blockDim.x) dst[x] = records[x];
-  __threadfence_system();                     // this thread's stores are visible system-wide before the flag
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  __syncthreads();                            // the CTA's stores happen-before thread 0's fence (bar.sync), and a
+  if (threadIdx.x == 0) {                     // system-scope fence is cumulative: ONE fence per CTA, not 256
+    __threadfence_system();
     volatile uint32_t* flag = win + flag_offset(slot, rank, world, rec_total);
     *flag = seq;
   }
@@ -111,6 +111,54 @@ merge_published_kernel(const uint32_t* __restrict__ window, uint32_t world, uint
     uint32_t v = 0;
     for (uint32_t r = 0; r < world; r++) {
       const uint32_t y = __ldcv(window + data_offset(slot, r, world, rec_total) + x);
+      v = is_sum ? v + y : (v | y);
+    }
+    out[x] = v;
+  }
+}
+
+// publish(seq) and merge(seq - 1) in ONE launch: CTAs [0, world) publish, the rest merge the previous batch.
+__global__ void __launch_bounds__(256)
+exchange_step_kernel(const uint32_t* __restrict__ records, uint32_t* const* __restrict__ peers, uint32_t rank,
+                     uint32_t world, uint32_t rec_total, uint32_t rec_words, uint32_t slot, uint32_t seq,
+                     const uint32_t* __restrict__ window, uint32_t prev_slot, uint32_t prev_seq,
+                     uint32_t* __restrict__ out, uint32_t* __restrict__ error) {
+  if (blockIdx.x < world) {
+    uint32_t* win = peers[blockIdx.x];
+    uint32_t* dst = win + data_offset(slot, rank, world, rec_total);
+    for (uint32_t x = threadIdx.x; x < rec_total; x += blockDim.x) dst[x] = records[x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      volatile uint32_t* flag = win + flag_offset(slot, rank, world, rec_total);
+      *flag = seq;
+    }
+    return;
+  }
+  if (prev_seq == 0) return;
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const volatile uint32_t* flag = window + flag_offset(prev_slot, threadIdx.x, world, rec_total);
+    const long long t0 = clock64();
+    while (int32_t(*flag - prev_seq) < 0) {
+      if (clock64() - t0 > kSpinLimitCycles) { s_ok = 0; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (!s_ok) {
+    if (threadIdx.x == 0) atomicExch(error, prev_seq);
+    return;
+  }
+  __threadfence_system();
+  const uint32_t mb = blockIdx.x - world, nmb = gridDim.x - world;
+  for (uint32_t x = mb * blockDim.x + threadIdx.x; x < rec_total; x += nmb * blockDim.x) {
+    const bool is_sum = (x % rec_words) < 2;
+    uint32_t v = 0;
+    for (uint32_t r = 0; r < world; r++) {
+      const uint32_t y = __ldcv(window + data_offset(prev_slot, r, world, rec_total) + x);
       v = is_sum ? v + y : (v | y);
     }
     out[x] = v;
@@ -230,6 +278,22 @@ SCN_API int scn_exchange_publish(scn_exchange* x, const uint32_t* d_records, voi
   const uint64_t seq = ++x->seq;
   publish_records_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_records, x->d_peer, x->rank, x->world, x->rec_total, uint32_t(seq % kSlots), uint32_t(seq));
+  SCN_XCUDA(cudaGetLastError());
+  if (seq_out) *seq_out = seq;
+  return SCN_OK;
+}
+
+SCN_API int scn_exchange_step(scn_exchange* x, const uint32_t* d_records, uint32_t* d_merged_previous, void* stream,
+                              uint64_t* seq_out) {
+  if (!x || !d_records || !d_merged_previous) return scn::api_fail(SCN_ERR_INVALID, "exchange_step: NULL argument");
+  if (!x->connected) return scn::api_fail(SCN_ERR_INVALID, "exchange_step: peers are not connected");
+  SCN_XCUDA(cudaSetDevice(x->device));
+  const uint64_t seq = ++x->seq;
+  uint32_t mgrid = (x->rec_total + 255) / 256;
+  if (mgrid > 16) mgrid = 16;
+  exchange_step_kernel<<<x->world + mgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_records, x->d_peer, x->rank, x->world, x->rec_total, x->rec_words, uint32_t(seq % kSlots), uint32_t(seq),
+      x->window, uint32_t((seq - 1) % kSlots), uint32_t(seq - 1), d_merged_previous, x->d_error);
   SCN_XCUDA(cudaGetLastError());
   if (seq_out) *seq_out = seq;
   return SCN_OK;

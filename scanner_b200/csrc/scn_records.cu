@@ -75,7 +75,13 @@ cudaError_t launch_summarize(const uint32_t* masks, const uint32_t* counts, uint
   cudaError_t e = cudaMemsetAsync(records, 0, sizeof(uint32_t) * size_t(n_steps) * (words + 2), stream);
   if (e != cudaSuccess) return e;
   if (n_spectra == 0) return cudaSuccess;
-  uint32_t splits = uint32_t(4 * num_sms) / (n_steps ? n_steps : 1);
+  // CTAs per step: spread 4 x SMs CTAs over the steps this batch actually TOUCHES (a rank of an 8-GPU sweep holds
+  // ~1/8 of the steps: dividing by n_steps left 7 x 11 CTAs to read all the masks, and the kernel -- 15 us on one
+  // GPU -- took ~100 us per batch at 8 GPUs, which was most of the weak-scaling loss the driver measured).
+  const uint64_t last_unit = first_unit + n_spectra - 1;
+  uint32_t touched = uint32_t(last_unit / units_per_step - first_unit / units_per_step) + 1;
+  if (touched > n_steps) touched = n_steps;
+  uint32_t splits = uint32_t(4 * num_sms) / (touched ? touched : 1);
   if (splits < 1) splits = 1;
   const uint32_t max_useful = (units_per_step + 63) / 64;
   if (splits > max_useful) splits = max_useful ? max_useful : 1;

@@ -70,6 +70,36 @@ def test_ranks_on_one_device_publish_then_merge_previous(world):
         x.close()
 
 
+def test_step_is_publish_plus_merge_of_the_previous_batch():
+    """scn_exchange_step: one launch that publishes batch i and merges batch i - 1 (the steady-state call of bench.py)."""
+    import torch
+    world, n_steps, rw = 3, 50, 66
+    xs = [S.RecordExchange(0, r, world, n_steps, rw) for r in range(world)]
+    S.RecordExchange.connect_local(xs)
+    rng = np.random.default_rng(17)
+    d_out = [torch.full((n_steps, rw), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    want = {}
+    for batch in range(1, 8):
+        parts = [rng.integers(0, 2 ** 20, (n_steps, rw), dtype=np.int64).astype(np.uint32) for _ in range(world)]
+        want[batch] = merge_rule(parts)
+        for r in range(world):
+            assert xs[r].step(torch.from_numpy(parts[r].view(np.int32)).cuda().data_ptr(), d_out[r].data_ptr()) == batch
+        torch.cuda.synchronize()
+        # rank r's step(batch) ran before ranks > r published `batch`, but every rank had published batch - 1
+        for r in range(world):
+            got = d_out[r].cpu().numpy().view(np.uint32)
+            if batch == 1:
+                assert np.all(got == 0xFFFFFFFF)          # nothing to merge yet: output untouched
+            else:
+                assert np.array_equal(got, want[batch - 1]), (batch, r)
+    for r in range(world):
+        xs[r].merge(7, d_out[r].data_ptr())
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert np.array_equal(d_out[r].cpu().numpy().view(np.uint32), want[7]) and xs[r].status() == 0
+        xs[r].close()
+
+
 def test_unconnected_exchange_refuses_to_publish():
     import torch
     x = S.RecordExchange(0, 0, 2, 4, 10)
