@@ -450,9 +450,13 @@ def main() -> None:
                           device=local_rank, ticket_slots=3)
     words, rec_words = ctx.words, ctx.record_words
     d_spec = torch.empty((n_spectra, n), dtype=torch.float32, device=dev) if spectrum else None
-    # masks / counts are double-buffered: batch i's are summarised on the side stream while batch i+1 is computed
-    d_masks = [torch.empty((n_spectra, words), dtype=torch.int32, device=dev) for _ in range(2)]
-    d_counts = [torch.empty((n_spectra,), dtype=torch.int32, device=dev) for _ in range(2)]
+    # masks / counts are TRIPLE-buffered.  The side-stream work of batch i (summarize + exchange) cannot get an SM while
+    # the persistent fused kernel of batch i+1 owns them all, so it really runs at the NEXT boundary, next to the start
+    # of batch i+2; with two buffers batch i+2 had to wait for it (it reuses batch i's buffers) and the whole side
+    # stream was serialised into every step; with three it only waits for batch i-1's, which finished a step ago.
+    NBUF = 3
+    d_masks = [torch.empty((n_spectra, words), dtype=torch.int32, device=dev) for _ in range(NBUF)]
+    d_counts = [torch.empty((n_spectra,), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     d_mask, d_count = d_masks[0], d_counts[0]
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
@@ -469,22 +473,22 @@ def main() -> None:
     xch = None
     if world > 1 and args.exchange == "peer":
         xch = S.open_record_exchange(local_rank, rank, world, n_steps, rec_words)
-    d_recs = [torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)]
-    d_gathers = [torch.empty((world, n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(2)] \
+    d_recs = [torch.empty((n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(NBUF)]
+    d_gathers = [torch.empty((world, n_steps, rec_words), dtype=torch.int32, device=dev) for _ in range(NBUF)] \
         if (world > 1 and xch is None) else None
     side = torch.cuda.Stream(device=dev, priority=-1)
-    out_ready = [torch.cuda.Event() for _ in range(2)]
-    out_free = [torch.cuda.Event() for _ in range(2)]
+    out_ready = [torch.cuda.Event() for _ in range(NBUF)]
+    out_free = [torch.cuda.Event() for _ in range(NBUF)]
     step_no = [0]
     last_seq = [0]
 
     kernel_events = []
 
     def step(timed: bool) -> None:
-        par = step_no[0] & 1
+        par = step_no[0] % NBUF
         step_no[0] += 1
-        if step_no[0] > 2:
-            stream.wait_event(out_free[par])                         # batch i-2's masks / counts have been summarised
+        if step_no[0] > NBUF:
+            stream.wait_event(out_free[par])                         # batch i-3's masks / counts have been summarised
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -590,7 +594,7 @@ def main() -> None:
     if world > 1:
         if xch is not None and xch.status() != 0:
             raise SystemExit(f"bench.py: record exchange timed out waiting for a peer (sequence {xch.status()})")
-        local = d_recs[(step_no[0] - 1) & 1]
+        local = d_recs[(step_no[0] - 1) % NBUF]
         sums = local[:, :2].clone().to(torch.int64)
         ors = local[:, 2:].clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
