@@ -314,7 +314,7 @@ def plugin_surface(wl: dict) -> dict:
         return {"unavailable": "scanner_b200/scan_b200 not built"}
     n, kind = wl["n"], wl["kind"]
     cores = os.cpu_count() or 1
-    producers = max(1, min(6, cores // 3))
+    producers = max(1, min(4, cores // 4))       # 4 producers + 2 workers measured best on 16- and 24-core hosts
 
     def run(total, workers, max_batch, prod, append, linger):
         cmd = [tool, "bench", str(kind), str(n), str(wl["enob"]), "1" if wl["dc"] else "0", "4096", str(total),

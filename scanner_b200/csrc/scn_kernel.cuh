@@ -87,7 +87,10 @@ struct WorkQueue {
   // (zero & threadIdx.x) makes the address lane-dependent as far as ptxas can tell, so it emits a plain ATOMG whose
   // result lands in a register nobody reads until the caller needs the index.
   // (Kernel time did not move in the A/B -- the other warp of the scheduler filled the gap -- but the stall is gone.)
-  __device__ __forceinline__ uint32_t take() { return 2u * takers + atomicAdd(w + (zero & threadIdx.x), 1u); }
+  // take() returns the RAW counter value; the caller adds first_dynamic() where it consumes the ticket (an add right
+  // here would wait for the atomic just like the SHFL did).
+  __device__ __forceinline__ uint32_t take() { return atomicAdd(w + (zero & threadIdx.x), 1u); }
+  __device__ __forceinline__ uint32_t first_dynamic() const { return 2u * takers; }
   // called once per taker, after its last take() has returned
   __device__ __forceinline__ void retire() {
     if (atomicAdd(w + 1, 1u) == takers - 1u) { atomicExch(w, 0u); atomicExch(w + 1, 0u); }
@@ -579,7 +582,7 @@ spectrum_sense_kernel(const KernelParams p) {
       if constexpr (kDC) {
         if (has_next) { int si, sq; raw.sums(si, sq); reduce_dc(si, sq, sred + tpar * (2 * G::RED_SLOTS)); }
       }
-      if (tid == 0) swork[spar] = ticket;
+      if (tid == 0) swork[spar] = ticket + wq.first_dynamic();
       __syncthreads();
       g_after2 = swork[spar];
       if constexpr (kDC) {

@@ -436,7 +436,7 @@ spectrum_sense_p64_kernel(const KernelParams p) {
           if (lane == 0) { sred[2 * G::WARPS * tpar + 2 * warp] = si; sred[2 * G::WARPS * tpar + 2 * warp + 1] = sq; }
         }
       }
-      if (t == 0) swork[spar] = ticket;
+      if (t == 0) swork[spar] = ticket + wq.first_dynamic();
       __syncthreads();
       s_after2 = swork[spar];
       if constexpr (kDC) {

@@ -131,9 +131,7 @@ __host__ __device__ constexpr int dft64_out_index(int slot) { return (slot >> 3)
 #ifndef SCN_WPT_MINCTAS
 #define SCN_WPT_MINCTAS 4
 #endif
-#ifndef SCN_WPT_GROUPMAX
-#define SCN_WPT_GROUPMAX 0
-#endif
+
 
 template <bool DC>
 __global__ void __launch_bounds__(32 * kWptWarpsPerCta, SCN_WPT_MINCTAS)
@@ -237,34 +235,6 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     float* out = p.spectra ? p.spectra + size_t(s_cur) * N + lane : nullptr;
     float* stash = reinterpret_cast<float*>(tile);
     uint32_t hb_lo = 0, hb_hi = 0;                 // hit bits by slot s
-#if SCN_WPT_GROUPMAX
-    // Two-level threshold test: one running maximum per group of 8 slots (1 FMNMX per bin instead of a compare and two
-    // predicated instructions), and the per-slot test only inside a group whose maximum is above the threshold (rare).
-    // fmaxf ignores NaN, as the strict > does (process.cpp:54).
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-      float db[8];
-      float gmax = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int s = 8 * g + i;
-        const float2 sq2 = __fmul2_rn(v[s], v[s]);
-        db[i] = kDbPerLog2 * __log2f(__fadd_rn(sq2.x, sq2.y));
-        if (out) out[32 * dft64_out_index(s)] = db[i];
-        gmax = fmaxf(gmax, db[i]);
-      }
-      if (gmax > p.threshold) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int s = 8 * g + i;
-          if (db[i] > p.threshold) {
-            stash[lane + 32 * s] = db[i];
-            if (s < 32) hb_lo |= 1u << s; else hb_hi |= 1u << (s - 32);
-          }
-        }
-      }
-    }
-#else
 #pragma unroll
     for (int s = 0; s < 64; s++) {
       const float2 sq2 = __fmul2_rn(v[s], v[s]);
@@ -275,7 +245,8 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
         if (s < 32) hb_lo |= 1u << s; else hb_hi |= 1u << (s - 32);
       }
     }
-#endif
+    // (a two-level test -- running maximum per group of 8 slots, per-slot compares only in a group above the threshold
+    //  -- executes ~80 fewer instructions per transform and measured 1.2 % SLOWER at the bench's hit rate; removed)
     uint32_t w_lo = 0, w_hi = 0;                   // mask words `lane` and `lane + 32` of this spectrum
     uint32_t total = 0;
     uint32_t any_lo = __reduce_or_sync(0xffffffffu, hb_lo), any_hi = __reduce_or_sync(0xffffffffu, hb_hi);
@@ -337,7 +308,7 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
     s_cur = s_next;
     // keep the broadcast of the ticket HERE, behind the epilogue's stores (see WorkQueue::take)
     asm volatile("" : "+r"(ticket) : : "memory");
-    s_next = __shfl_sync(0xffffffffu, ticket, 0);
+    s_next = __shfl_sync(0xffffffffu, ticket, 0) + wq.first_dynamic();
   }
   if (lane == 0) wq.retire();
 }
