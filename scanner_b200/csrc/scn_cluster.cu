@@ -30,6 +30,10 @@
 #include "scn_dispatch.h"
 #include "scn_wpt.cuh"
 
+#ifndef SCN_CL_PRE_F32
+#define SCN_CL_PRE_F32 16      // fp32 IQ: how many of the 32 raw loads per thread are issued one buffer ahead
+#endif
+
 namespace scn {
 
 constexpr int kClM = 4096;                       // row length
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
   // phase 2 (whose register need is small), so their HBM latency hides behind phase 2 and the epilogue; fp32 IQ keeps
   // only half of them in registers that long (K > 1: none, 64 accumulators), the rest loads in place.
   constexpr int kRawWords = KIND == SCN_KIND_FLOAT_COMPLEX ? 4 : KIND == SCN_KIND_BYTE_COMPLEX ? 1 : 2;
-  constexpr int kPre = KIND == SCN_KIND_FLOAT_COMPLEX ? (AVG ? 0 : 16) : 32;
+  constexpr int kPre = KIND == SCN_KIND_FLOAT_COMPLEX ? (AVG ? 0 : SCN_CL_PRE_F32) : 32;
   const uint32_t lhalf = uint32_t(tid) & 1u, n2base = uint32_t(tid) >> 1;
   uint32_t rawv[32][kRawWords];
   auto load_raw = [&](const uint8_t* buf, int u_begin, int u_end) {

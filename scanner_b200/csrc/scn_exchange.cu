@@ -68,13 +68,24 @@ __host__ __device__ inline size_t flag_offset(uint32_t slot, uint32_t row, uint3
   return size_t(kSlots) * world * rec_total + size_t(slot) * world + row;
 }
 
+// One CTA's copy of a record table into a (peer) window: 8-byte stores when the table length allows (NVLink stores are
+// fire-and-forget, so the instruction count is what matters: cfg4's table is 137 KB per rank).
+__device__ __forceinline__ void copy_records(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n) {
+  if ((n & 1u) == 0u && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 7u) == 0u) {
+    uint2* d2 = reinterpret_cast<uint2*>(dst);
+    const uint2* s2 = reinterpret_cast<const uint2*>(src);
+    for (uint32_t x = threadIdx.x; x < n / 2; x += blockDim.x) d2[x] = s2[x];
+  } else {
+    for (uint32_t x = threadIdx.x; x < n; x += blockDim.x) dst[x] = src[x];
+  }
+}
+
 // grid = world CTAs: CTA d copies this rank's records into peer d's window and then raises its flag there.
 __global__ void __launch_bounds__(256)
 publish_records_kernel(const uint32_t* __restrict__ records, uint32_t* const* __restrict__ peers, uint32_t rank,
                        uint32_t world, uint32_t rec_total, uint32_t slot, uint32_t seq) {
   uint32_t* win = peers[blockIdx.x];
-  uint32_t* dst = win + data_offset(slot, rank, world, rec_total);
-  for (uint32_t x = threadIdx.x; x < rec_total; x += blockDim.x) dst[x] = records[x];
+  copy_records(win + data_offset(slot, rank, world, rec_total), records, rec_total);
   __syncthreads();                            // the CTA's stores happen-before thread 0's fence (bar.sync), and a
   if (threadIdx.x == 0) {                     // system-scope fence is cumulative: ONE fence per CTA, not 256
     __threadfence_system();
@@ -118,15 +129,14 @@ merge_published_kernel(const uint32_t* __restrict__ window, uint32_t world, uint
 }
 
 // publish(seq) and merge(seq - 1) in ONE launch: CTAs [0, world) publish, the rest merge the previous batch.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 exchange_step_kernel(const uint32_t* __restrict__ records, uint32_t* const* __restrict__ peers, uint32_t rank,
                      uint32_t world, uint32_t rec_total, uint32_t rec_words, uint32_t slot, uint32_t seq,
                      const uint32_t* __restrict__ window, uint32_t prev_slot, uint32_t prev_seq,
                      uint32_t* __restrict__ out, uint32_t* __restrict__ error) {
   if (blockIdx.x < world) {
     uint32_t* win = peers[blockIdx.x];
-    uint32_t* dst = win + data_offset(slot, rank, world, rec_total);
-    for (uint32_t x = threadIdx.x; x < rec_total; x += blockDim.x) dst[x] = records[x];
+    copy_records(win + data_offset(slot, rank, world, rec_total), records, rec_total);
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -289,9 +299,9 @@ SCN_API int scn_exchange_step(scn_exchange* x, const uint32_t* d_records, uint32
   if (!x->connected) return scn::api_fail(SCN_ERR_INVALID, "exchange_step: peers are not connected");
   SCN_XCUDA(cudaSetDevice(x->device));
   const uint64_t seq = ++x->seq;
-  uint32_t mgrid = (x->rec_total + 255) / 256;
-  if (mgrid > 16) mgrid = 16;
-  exchange_step_kernel<<<x->world + mgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  uint32_t mgrid = (x->rec_total + 511) / 512;
+  if (mgrid > 32) mgrid = 32;
+  exchange_step_kernel<<<x->world + mgrid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
       d_records, x->d_peer, x->rank, x->world, x->rec_total, x->rec_words, uint32_t(seq % kSlots), uint32_t(seq),
       x->window, uint32_t((seq - 1) % kSlots), uint32_t(seq - 1), d_merged_previous, x->d_error);
   SCN_XCUDA(cudaGetLastError());
