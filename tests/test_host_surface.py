@@ -145,3 +145,24 @@ def test_sweep_processor_equals_process_samples_on_every_gpu_count(exchange):
         assert m and int(m.group(2)) == hits and int(m.group(4)) == 3 and int(m.group(7)) == 8 * 12
         per_gpu = [int(x) for x in m.group(5).split()]
         assert len(per_gpu) == gpus and min(per_gpu) > 0
+
+
+@pytest.mark.gpu
+def test_batched_appends_from_several_producers_lose_nothing_on_the_gpu():
+    """The ingest path at speed: 4 producer threads x AppendSamplesBatch(64) -> ring slab -> 2 workers submitting the slab
+    runs with scn_submit_gather and reading results in place, against 1 producer x single AppendSamples: every buffer is
+    processed exactly once (same buffer and hit totals; K = 1 detection does not depend on order or batch shape)."""
+    def run(*extra):
+        out, _ = _run(["bench", "1", "2048", "8", "1", "64", "61440", *extra])
+        m = re.search(r"\((\d+) buffers .* (\d+) hits, (\d+) launches of which (\d+) straight", out)
+        assert m, out
+        return int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    base = run("1", "1024", "1", "1", "0")
+    many = run("2", "4096", "4", "64", "200")
+    assert base[0] == many[0] == 61440 and base[1] == many[1] and base[1] > 0
+    assert many[3] == many[2] > 0                       # every launch came straight from the pinned slab
+    staged = subprocess.run([TOOL, "bench", "1", "2048", "8", "1", "64", "61440", "2", "4096", "4", "64", "200"],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=dict(os.environ, SCN_STAGING_COPY="1"))
+    assert staged.returncode == 0
+    m = re.search(r"\((\d+) buffers .* (\d+) hits, (\d+) launches of which (\d+) straight", staged.stdout.decode())
+    assert m and int(m.group(2)) == base[1] and int(m.group(4)) == 0
