@@ -20,6 +20,13 @@
  *                          ProcessSamples::ThreadWorker's FrequencyDomain branch,
  *                          process.cpp:292-299, applied to a batch of queue messages
  *   scn_submit/collect  <- the same, asynchronous (tickets), for the ThreadWorker loop
+ *   scn_submit_gather / scn_collect_view
+ *                       <- the same without host copies: the batch is handed over as address runs of the queue's
+ *                          pinned slab (what replaces the per-message memcpy of process.cpp:293-295) and the results
+ *                          are read in place
+ *   scn_exchange_* / scn_nccl_gather_*
+ *                       <- no reference counterpart (process.cpp:316-331 runs two threads on one FFT): the per-sweep
+ *                          exchange of per-retune-step records between the GPUs that share a sweep
  *   scn_launch_device   <- the same on buffers already resident in HBM
  *   scn_hit_frequency   <- the Hz mapping inside process_fft, process.cpp:38-39,55
  *   scn_use_window      <- m_useWindow initialiser, process.cpp:85
@@ -94,7 +101,7 @@ typedef struct scn_hit {
 
 typedef struct scn_config {
   int32_t device;               /* CUDA ordinal */
-  uint32_t sample_count;        /* N: FFT size == samples per buffer (process.cpp:78); power of two, 256..65536 (above 16384: four-step path through an HBM intermediate) */
+  uint32_t sample_count;        /* N: FFT size == samples per buffer (process.cpp:78); power of two, 256..65536 (2^14..2^16: one transform per thread-block cluster, single HBM pass) */
   uint32_t sample_rate;         /* Hz (process.cpp:79) */
   uint32_t enob;                /* effective number of bits (scan.cpp:138,183,196) */
   uint32_t sample_kind;         /* SCN_KIND_* */

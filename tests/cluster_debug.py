@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Developer tool: one small run of the cluster kernel through the host path against the oracle (for compute-sanitizer)."""
+"""Test infrastructure (lives under tests/ because it uses the oracle): one small run of the cluster kernel through the host
+path against the oracle, printable and short enough to run under compute-sanitizer.  usage: cluster_debug.py <kind> <log2n> <dc> <K>"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

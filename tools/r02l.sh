@@ -2,7 +2,7 @@
 L=gpurun_out/r02l.log; : > $L
 for a in "1 14 0 1" "4 14 0 1" "4 15 0 1" "4 16 0 1" "3 16 1 2" "2 15 1 1" "1 16 1 1"; do
   echo "== $a" >> $L
-  timeout 200 python tools/cluster_debug.py $a 2>&1 | tail -4 >> $L
+  timeout 200 python tests/cluster_debug.py $a 2>&1 | tail -4 >> $L
 done
 timeout 400 python -m pytest tests/test_gpu_large.py -m gpu -q 2>&1 | tail -8 >> $L
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "14" 2>&1 | tail -5 >> $L
