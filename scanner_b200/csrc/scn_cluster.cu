@@ -53,7 +53,9 @@ struct ClusterSmem {
   int32_t dcsum[2 * 4];                          // [cta][I, Q]
   int32_t red[2 * 8];                            // per-warp partial sums
   uint32_t total;
+  uint64_t bar[4];                               // mbarriers: kBarReady, kBarRows, kBarDc, kBarTable
 };
+enum { kBarReady = 0, kBarRows = 1, kBarDc = 2, kBarTable = 3 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -62,18 +64,26 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// arrive without the release fence: for barriers that only order earlier READS against later remote writes
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_shared(const void* p, uint32_t rank) {       // address of `p` in CTA `rank`'s smem
   uint32_t out;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
   return out;
 }
-__device__ __forceinline__ void st_cluster(uint32_t addr, float2 v) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+// Remote stores are ASYNC stores that count their bytes on an mbarrier in the destination CTA (STAS): the receiver
+// waits for its own mbarrier phase, so no release/acquire cluster barrier is needed around an exchange.  That matters:
+// barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU (waits for every outstanding GLOBAL store of the CTA, i.e.
+// the spectrum rows just written) and barrier.cluster.wait to CCTL.IVALL (drops the L1 lines holding window and
+// twiddles) -- together 10-15 % of all stall samples of the first version of this kernel (profiles/r02m_ncu_cl16_*).
+__device__ __forceinline__ void st_async(uint32_t addr, float2 v, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(addr), "f"(v.x), "f"(v.y), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void st_cluster(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void st_async(uint32_t addr, uint32_t v, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(bar) : "memory");
+}
+// arrive on a peer's mbarrier without a fence: orders nothing but "this warp got here" (used for "done READING")
+__device__ __forceinline__ void mbar_arrive_peer_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // twiddle tables (host: scn_api.cu, layout 3):
@@ -202,6 +212,17 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
     if (slot < 32) cand_lo |= (cand ? 1u : 0u) << slot; else cand_hi |= (cand ? 1u : 0u) << (slot - 32);
   }
 
+  uint32_t ph_ready = 0, ph_rows = 0, ph_dc = 0, ph_table = 0;      // mbarrier phase parities
+  if constexpr (C > 1) {
+    if (tid == 0) {
+      mbar_init(&sm.bar[kBarReady], 8u * C);         // one arrival per warp of every CTA
+      mbar_init(&sm.bar[kBarRows], 1);               // thread 0's expect_tx + the bytes of the other CTAs
+      mbar_init(&sm.bar[kBarDc], 1);
+      mbar_init(&sm.bar[kBarTable], 1);
+    }
+    cluster_arrive();                                // every CTA's mbarriers exist before anyone signals them
+    cluster_wait();
+  }
   float acc[AVG ? 64 : 1];
   if (cluster_id < p.n_spectra && kPre > 0) load_raw(buffer_ptr(cluster_id, 0), 0, kPre);
   for (uint32_t s = cluster_id; s < p.n_spectra; s += n_clusters) {
@@ -220,11 +241,17 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
           int ti = 0, tq = 0;
 #pragma unroll
           for (int w = 0; w < 8; w++) { ti += sm.red[2 * w]; tq += sm.red[2 * w + 1]; }
-          st_cluster(map_shared(&sm.dcsum[2 * crank], uint32_t(tid)), uint32_t(ti));
-          st_cluster(map_shared(&sm.dcsum[2 * crank + 1], uint32_t(tid)), uint32_t(tq));
+          if constexpr (C == 1) {
+            sm.dcsum[0] = ti; sm.dcsum[1] = tq;
+          } else {
+            if (tid == 0) mbar_expect_tx(&sm.bar[kBarDc], 8u * C);         // two ints from each CTA (this one included)
+            const uint32_t rbar = map_shared(&sm.bar[kBarDc], uint32_t(tid));
+            st_async(map_shared(&sm.dcsum[2 * crank], uint32_t(tid)), uint32_t(ti), rbar);
+            st_async(map_shared(&sm.dcsum[2 * crank + 1], uint32_t(tid)), uint32_t(tq), rbar);
+          }
         }
-        cluster_arrive();
-        cluster_wait();
+        if constexpr (C == 1) __syncthreads();
+        else { mbar_wait(&sm.bar[kBarDc], ph_dc); ph_dc ^= 1u; }
         int ti = 0, tq = 0;
 #pragma unroll
         for (int c = 0; c < C; c++) { ti += sm.dcsum[2 * c]; tq += sm.dcsum[2 * c + 1]; }
@@ -249,7 +276,6 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < 64; r++) v[r] = row[t + 65 * r];
-      if constexpr (C > 1) cluster_arrive_relaxed();     // this CTA is done reading its rows (wait: before the exchange)
       {
         // v[8a + b] *= W_N^(n1 t) * W_4096^(t (8a + b)); the thread constant rides on the w^(8a) factors
         const float2* tw = twA + t;
@@ -268,10 +294,18 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
           for (int b = 1; b < 8; b++) v[8 * a + b] = cmul(v[8 * a + b], cmul(wa, wb[b]));
         }
       }
+      if constexpr (C > 1) {                             // this warp is done reading its row (the values were consumed
+        __syncwarp();                                    // above): tell every CTA of the cluster, this one included
+        if (lane < C) mbar_arrive_peer_relaxed(map_shared(&sm.bar[kBarReady], uint32_t(lane)));
+      }
       dft64_inplace(v);                                  // slot x: A[n1][k2 = t + 64 q] * W_N^(n1 t), q = dft64_out_index(x)
       // ---- exchange: slot (t, q) -> S[n1][t + 64 (q mod 64/C)] in the CTA that owns k2 = t + 64 q ---------------------
-      if constexpr (C > 1) cluster_wait();               // every CTA of the cluster has finished reading its rows
-      else __syncthreads();
+      if constexpr (C > 1) {                             // every warp of every CTA of the cluster has finished reading
+        mbar_wait(&sm.bar[kBarReady], ph_ready); ph_ready ^= 1u;
+        if (tid == 0) mbar_expect_tx(&sm.bar[kBarRows], uint32_t(C - 1) * kClThreads * (64 / C) * uint32_t(sizeof(float2)));
+      } else {
+        __syncthreads();
+      }
       {
         const float2* tb = twB + n1 * 64;
         float2* own = rows + size_t(n1) * KL + t;        // S[n1][t + 64 (q mod QPC)] of whichever CTA owns q
@@ -284,17 +318,17 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
               if (dft64_out_index(x) / QPC == c)
                 own[64 * (dft64_out_index(x) % QPC)] = cmul(v[x], __ldg(tb + dft64_out_index(x)));   // times W_N^(64 n1 q)
           } else {
-            const uint32_t dst = map_shared(own, uint32_t(c));
+            const uint32_t dst = map_shared(own, uint32_t(c)), rbar = map_shared(&sm.bar[kBarRows], uint32_t(c));
 #pragma unroll
             for (int x = 0; x < 64; x++)
               if (dft64_out_index(x) / QPC == c)
-                st_cluster(dst + uint32_t(sizeof(float2)) * 64u * uint32_t(dft64_out_index(x) % QPC),
-                           cmul(v[x], __ldg(tb + dft64_out_index(x))));
+                st_async(dst + uint32_t(sizeof(float2)) * 64u * uint32_t(dft64_out_index(x) % QPC),
+                         cmul(v[x], __ldg(tb + dft64_out_index(x))), rbar);
           }
         }
       }
-      cluster_arrive();
-      cluster_wait();                                    // S is complete in every CTA
+      __syncthreads();                                   // this CTA's own share
+      if constexpr (C > 1) { mbar_wait(&sm.bar[kBarRows], ph_rows); ph_rows ^= 1u; }   // ... and everyone else's: S is complete
       if constexpr (kPre > 0) {                          // next buffer's loads go in flight behind phase 2 + epilogue
         uint32_t ns = s, nk = k + 1;
         if (nk == K) { nk = 0; ns = s + n_clusters; }
@@ -381,10 +415,18 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
             p.masks[size_t(s) * (N / 32) + word0 + w0 + lane] = mw;
           }
         }
-        if (lane < C) st_cluster(map_shared(&sm.table[k1 * 4 + crank], uint32_t(lane)), run);
+        if constexpr (C == 1) {
+          if (lane == 0) sm.table[k1 * 4] = run;
+        } else if (lane < C) {
+          st_async(map_shared(&sm.table[k1 * 4 + crank], uint32_t(lane)), run, map_shared(&sm.bar[kBarTable], uint32_t(lane)));
+        }
       }
-      cluster_arrive();
-      cluster_wait();
+      if constexpr (C == 1) {
+        __syncthreads();
+      } else {
+        if (tid == 0) mbar_expect_tx(&sm.bar[kBarTable], uint32_t(R * C) * 4u);   // R counts from each CTA (this one included)
+        mbar_wait(&sm.bar[kBarTable], ph_table); ph_table ^= 1u;
+      }
       // ranks: shifted-bin order is (k1 ^ R/2) major, owner CTA minor
       if (tid < R) {
         const uint32_t mine = uint32_t(tid) ^ uint32_t(R / 2);
@@ -423,8 +465,10 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
     }
   }
   // no CTA may exit while a peer can still address its shared memory
-  cluster_arrive();
-  cluster_wait();
+  if constexpr (C > 1) {
+    cluster_arrive();
+    cluster_wait();
+  }
 }
 
 template <int C, int KIND>
