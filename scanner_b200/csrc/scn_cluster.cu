@@ -15,14 +15,15 @@
 //            the inter-stage twiddle W_N^(n1 k2) = W_N^(n1 t) * W_N^(64 n1 q) folded in (first factor into the row FFT's
 //            own twiddles, second one multiply per output);
 //   exchange CTA c'' owns k2 in [c'' M/C, (c''+1) M/C): every thread stores its 64 outputs into the owner's shared
-//            memory (st.shared::cluster; 3/4 of them cross SMs when C = 4) as S[n1][k2 local] -- the row buffers are
-//            dead by then and are reused as S;
+//            memory (st.async with mbarrier completion; 3/4 of them cross SMs when C = 4) as S[n1][k2 local] -- the
+//            row buffers are dead by then and are reused as S;
 //   phase 2  per k2 one radix-R DFT over n1 (R = 4, 8, 16) -> X[k2 + M k1], |X|^2, K-average, dB (utility.cpp:86-98),
 //            detection (process.cpp:46-61).  For fixed k1 a warp holds 32 consecutive bins: coalesced stores, one
 //            mask word per ballot.
 //   epilogue hit records must be ordered over the WHOLE spectrum: per-(k1, CTA) hit counts are exchanged over DSMEM
 //            and prefix-summed in shifted-bin order.
-// Three cluster barriers per buffer (+1 with DC correction), split arrive / wait where independent work exists.
+// Synchronisation inside the loop is mbarriers only (rows read / rows arrived / DC sums / hit-count table), see st_async
+// below; cluster barriers only after mbarrier init and before exit.
 // Same results contract as every other size (tests/test_gpu_large.py, tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
