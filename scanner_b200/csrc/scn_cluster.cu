@@ -330,10 +330,21 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
       }
       __syncthreads();                                   // this CTA's own share
       if constexpr (C > 1) { mbar_wait(&sm.bar[kBarRows], ph_rows); ph_rows ^= 1u; }   // ... and everyone else's: S is complete
-      if constexpr (kPre > 0) {                          // next buffer's loads go in flight behind phase 2 + epilogue
+      {                                                  // next buffer's loads go in flight behind phase 2 + epilogue
         uint32_t ns = s, nk = k + 1;
         if (nk == K) { nk = 0; ns = s + n_clusters; }
-        if (ns < p.n_spectra) load_raw(buffer_ptr(ns, nk), 0, kPre);
+        if (ns < p.n_spectra) {
+          const uint8_t* nb = buffer_ptr(ns, nk);
+          if constexpr (kPre > 0) load_raw(nb, 0, kPre);
+          if constexpr (kPre < 32) {
+            // the loads that have no registers to wait in (u >= kPre, i.e. the upper (32 - kPre)/32 of the buffer,
+            // contiguous): one thread asks the copy engine to pull this CTA's 1/C of them into L2 -- no LSU work
+            if (tid == 0) {
+              constexpr uint32_t kBegin = uint32_t(N) * kBytes / 32u * kPre, kShare = (uint32_t(N) * kBytes - kBegin) / C;
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nb + kBegin + crank * kShare), "r"(kShare) : "memory");
+            }
+          }
+        }
       }
 
       // ---- phase 2: radix-R over n1 for k2 = crank KL + tid + 256 u; power; K-average ----------------------------------

@@ -24,3 +24,29 @@ print("\n## hottest instructions")
 hot = sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:25]
 for r in hot:
     print("%6s  %s" % (r[ix["# Samples"]], r[ix["Source"]].strip()[:100]))
+# samples per barrier-delimited section of the SASS (program order): which PHASE of the kernel the time goes to
+print("\n## samples by barrier-delimited SASS section (>= 1.5 % of all samples); ops = static count of the main opcodes")
+seg, segs = [], []
+for i, r in enumerate(data):
+    seg.append(r)
+    src = r[ix["Source"]].strip()
+    if re.search(r"\b(BAR\.SYNC|BAR\.RED|UCGABAR_WAIT|SYNCS\.PHASECHK)", src):
+        segs.append(seg); seg = []
+if seg: segs.append(seg)
+pos = 0
+for sg in segs:
+    smp = sum(int(r[ix["# Samples"]] or 0) for r in sg)
+    if smp >= 0.015 * max(total, 1):
+        ops = collections.Counter()
+        why = collections.Counter()
+        for r in sg:
+            src = r[ix["Source"]].strip()
+            op = (src.split()[0] if not src.startswith("@") else src.split()[1]).split(".")[0]
+            ops[op] += 1
+            for c in stall_cols:
+                v = int(r[ix[c]] or 0)
+                if v: why[c[6:]] += v
+        print("  sass rows %5d-%5d  %6d samples (%4.1f %%)  ops: %s | stalls: %s" % (
+            pos, pos + len(sg) - 1, smp, 100.0 * smp / total,
+            " ".join(f"{k}:{v}" for k, v in ops.most_common(7)), " ".join(f"{k}:{v}" for k, v in why.most_common(4))))
+    pos += len(sg)
