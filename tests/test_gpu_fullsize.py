@@ -36,11 +36,17 @@ def device_run(ss, raw_t, n_spectra, n, hit_cap):
     ("cfg3 int16 4096 K=64 x 24 steps x 6", 3, 12, False, 4096, 64, 24 * 6),
     ("cfg4 fp32 8192 x 133 steps x 8", 4, 0, False, 8192, 1, 133 * 8),
     ("cfg1 int16 1024 K=16 x 2000", 3, 12, False, 1024, 16, 2000),
+    # cluster kernel (scn_cluster.cu): several transforms per persistent cluster -- mbarrier phases flip, the next
+    # buffer is prefetched behind the current one, DSMEM regions are reused (148 / 74 / 37 clusters on a B200)
+    ("cfg5 fp32 2^16 x 100", 4, 0, False, 1 << 16, 1, 100),
+    ("cfg5 int8 2^15 DC x 230", 1, 8, True, 1 << 15, 1, 230),
+    ("cfg5 int16 2^14 K=3 x 330", 3, 12, True, 1 << 14, 3, 330),
+    ("cfg5 fp32 2^15 K=2 x 160", 4, 0, False, 1 << 15, 2, 160),
 ])
 def test_fullsize_properties(name, kind, enob, dc, n, K, n_spectra):
     dev = torch.device("cuda", 0)
     # a pool of distinct synthetic buffers, tiled to the full batch with a random map (keeps host generation cheap)
-    pool = synth.make_buffers(kind, n, 64 * K if K > 1 else 256, enob, seed=31 + n)
+    pool = synth.make_buffers(kind, n, (64 if n <= 8192 else 12) * K if K > 1 else (256 if n <= 8192 else 32), enob, seed=31 + n)
     rng = np.random.default_rng(7)
     pool_t = torch.from_numpy(pool).to(dev)
     per = pool.shape[0] // K                       # distinct spectra in the pool
@@ -75,7 +81,7 @@ def test_fullsize_properties(name, kind, enob, dc, n, K, n_spectra):
     floor = 10.0 * torch.log10(torch.sqrt((mag ** 2).mean(dim=1, keepdim=True))) - 10.0
     strong = (t64 >= floor)[pick_t]
     err = (spec.double() - t64[pick_t]).abs()
-    assert float(err[strong].max()) < 1e-3
+    assert float(err[strong].max()) < (1e-3 if n <= 8192 else 2e-3)     # one more twiddle stage above 2^13
     # Parseval per spectrum, straight from the raw samples (no FFT in the checker)
     w_t = torch.from_numpy(window.astype(np.float64)).to(dev)
     x = raw_t.double()
