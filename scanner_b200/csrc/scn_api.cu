@@ -475,9 +475,10 @@ SCN_API int scn_create(const scn_config* config, scn_ctx** out) {
   if (!td) {
     // N >= 2^14: one transform per thread-block cluster, single HBM pass (scn_cluster.cu).  SCN_FOUR_STEP=1 in the
     // environment selects the older four-step path through an HBM intermediate (kept for A/B and as a cross-check).
-    // (N = 2^14 int8 IQ stays on the 16-points-per-thread kernel: measured 261 vs 235 Gsamples/s.)
+    // (At N = 2^14 that older path is the 16-points-per-thread kernel; int8 IQ: 212 vs 278 Gsamples/s for the cluster
+    // kernel, profiles/r02zh_*.txt.)
     const bool four_step = std::getenv("SCN_FOUR_STEP") != nullptr;
-    const bool clustered = log2n >= 14 && !four_step && !(log2n == 14 && cf.sample_kind == SCN_KIND_BYTE_COMPLEX) &&
+    const bool clustered = log2n >= 14 && !four_step &&
         scn::variant_cluster(int(cf.sample_kind), log2n, cf.correct_dc_offset != 0, K > 1, &c->variant);
     c->large = !clustered && log2n > scn::kMaxLog2N;
     c->log2n2 = c->large ? log2n - 4 : log2n;
