@@ -26,7 +26,8 @@ def four_step(monkeypatch):
 
 
 @pytest.mark.parametrize("log2n,kind,enob,dc", [(15, S.KIND_BYTE_COMPLEX, 8, True), (16, S.KIND_FLOAT_COMPLEX, 0, False),
-                                                (16, S.KIND_SHORT_COMPLEX, 12, True)])
+                                                (16, S.KIND_SHORT_COMPLEX, 12, True),
+                                                (14, S.KIND_BYTE_COMPLEX, 8, True)])    # 2^14: the 16-point in-CTA kernel
 def test_four_step_path_parity(four_step, log2n, kind, enob, dc):
     run_case(kind, 1 << log2n, enob, dc, 1, 3, seed=700 + log2n * 10 + kind, acc_factor=4.0)
 
@@ -43,7 +44,8 @@ def test_cluster_kernel_is_the_default_large_path():
 
 
 @pytest.mark.parametrize("kind,enob,dc,K", [(S.KIND_FLOAT_COMPLEX, 0, False, 1), (S.KIND_SHORT_COMPLEX, 12, True, 3),
-                                            (S.KIND_SHORT, 12, False, 1)])
+                                            (S.KIND_SHORT, 12, False, 1), (S.KIND_BYTE_COMPLEX, 8, True, 1),
+                                            (S.KIND_BYTE_COMPLEX, 8, False, 2)])
 def test_cluster_kernel_single_cta_size(kind, enob, dc, K):
     run_case(kind, 1 << 14, enob, dc, K, 5, seed=640 + kind, acc_factor=4.0)        # C = 1: 4 rows x 4096 in one CTA
 
