@@ -75,3 +75,30 @@ def test_large_band_edges():
         if want:
             assert res["hits"]["bin"][s, 0] == i and abs(res["hits"]["power_db"][s, 0] - 10 * np.log10(n)) < 1e-3
             assert res["hit_mask"][s, i >> 5] == np.uint32(1 << (i & 31))
+
+
+def test_cluster_spectrum_pointer_alignment():
+    """The ABI only asks for a 16-byte aligned RAW pointer: a spectra pointer that is merely 4-byte aligned must give
+    the same bits and must not write outside its range (guards any future vector / bulk-store epilogue)."""
+    torch = pytest.importorskip("torch")
+    from tests import synth
+    n, ns = 1 << 15, 5
+    raw = synth.make_buffers(S.KIND_FLOAT_COMPLEX, n, ns, 0, seed=99)
+    dev = torch.device("cuda", 0)
+    raw_t = torch.from_numpy(raw).to(dev)
+    w = S.window_build(S.WIN_HANN, n)
+    with S.SpectrumSense(n, 8_000_000, 0, 12.0, w, sample_kind=S.KIND_FLOAT_COMPLEX, max_spectra=ns) as ss:
+        outs = []
+        for off in (0, 1, 4):                         # floats: 16-byte aligned, 4-byte aligned, 16-byte aligned again
+            buf = torch.zeros(ns * n + 8, dtype=torch.float32, device=dev)
+            mask = torch.zeros((ns, n // 32), dtype=torch.int32, device=dev)
+            cnt = torch.zeros((ns,), dtype=torch.int32, device=dev)
+            ss.launch_device(raw_t.data_ptr(), ns, buf.data_ptr() + 4 * off, mask.data_ptr(), cnt.data_ptr(), 0, 0,
+                             torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append((buf[off:off + ns * n].clone(), mask, cnt))
+            assert float(buf[:off].abs().sum()) == 0.0 and float(buf[off + ns * n:].abs().sum()) == 0.0
+    for o in outs[1:]:
+        assert torch.equal(o[0].view(torch.int32), outs[0][0].view(torch.int32))
+        assert torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+    assert int(outs[0][2].sum()) > 0
