@@ -20,11 +20,12 @@ constexpr int kWptN = 2048;
 constexpr int kWptWarpsPerCta = 2;
 // tile padding: 1 float2 per 64 -> lane stride 65 elements: conflict-free 64-bit scatter, unit-stride gather
 __host__ __device__ constexpr int wpt_tile_elems() { return kWptN + (kWptN / 64); }
-// The next transform's 4 KB of int8 IQ is prefetched into 32 registers right after the conversion.  Measured
-// alternatives on B200 (profiles/README.md), all removed: staging it with one TMA bulk copy per transform
-// (405 vs 450 Gsamples/s: 32 extra LDS per lane and a tighter register allocation), issuing the loads after the
-// pass-0 scatter (423), keeping the two warps of a CTA in lockstep for the instruction cache (+0.7 %, noise),
-// 5-6 CTAs per SM at 168 registers (371).
+// The next transform's 4 KB of int8 IQ is pulled into L2 by one bulk prefetch per warp (cp.async.bulk.prefetch.L2)
+// right after the conversion and loaded (L2 hits) at the top of its own iteration.  Measured alternatives on B200
+// (profiles/README.md), all removed: prefetching it into 32 registers one transform ahead (453 vs 458 Gsamples/s),
+// staging it with one TMA bulk copy per transform (405: 32 extra LDS per lane and a tighter register allocation),
+// issuing the loads after the pass-0 scatter (423), keeping the two warps of a CTA in lockstep for the instruction
+// cache (+0.7 %, noise), 5-6 CTAs per SM at 168 registers (371; 417 without the register prefetch).
 constexpr size_t kWptWarpBytes = sizeof(float2) * size_t(wpt_tile_elems());
 static_assert(kWptWarpBytes % 16 == 0, "warp region must keep 16-byte alignment");
 constexpr size_t kWptSmemBytes = kWptWarpBytes * kWptWarpsPerCta;
@@ -157,13 +158,16 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
   uint32_t raw[32];                                                  // row r: samples 2*lane, 2*lane+1 (+ 64 r)
   uint32_t s_cur = gw, s_next = gw + nw;
   if (s_cur >= p.n_spectra) { if (lane == 0) wq.retire(); return; }
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_cur) * N * 2) + lane;
-#pragma unroll
-    for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
-  }
 
   while (true) {
+    // raw samples of this transform.  They are NOT held in registers one transform ahead (32 registers per lane that
+    // the FFT's schedule can use better: +1 %, profiles/r02zm_wpt_l2_prefetch_ab.txt); instead the copy engine was asked
+    // one transform ago to pull these 4 KB into L2 (see below), so the loads are L2 hits.
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_cur) * N * 2) + lane;
+#pragma unroll
+      for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
+    }
     // ---- DC (warp-local), convert + window ---------------------------------------------------------------
     float2 negc = make_float2(-(kMagic + 128.0f), -(kMagic + 128.0f));
     if constexpr (DC) {
@@ -189,14 +193,13 @@ spectrum_sense_wpt_kernel(const KernelParams p) {
       v[r] = __fmul2_rn(__fadd2_rn(a, negc), make_float2(w2.x, w2.x));          // column 0, row r
       v[32 + r] = __fmul2_rn(__fadd2_rn(b, negc), make_float2(w2.y, w2.y));     // column 1, row r
     }
-    // ---- next transform's loads go in flight now; the index after it is requested from the work counter ----------
+    // ---- next transform: one bulk L2 prefetch of its 4 KB (UBLKPF.L2, no LSU work, no registers); the index after
+    // it is requested from the work counter ------------------------------------------------------------------------
     const bool has_next = s_next < p.n_spectra;
     uint32_t ticket = 0;
-    if (has_next) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw + size_t(s_next) * N * 2) + lane;
-#pragma unroll
-      for (int r = 0; r < 32; r++) raw[r] = ldg_stream(src + 32 * r);
-      if (lane == 0) ticket = wq.take();
+    if (has_next && lane == 0) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.raw + size_t(s_next) * N * 2), "r"(uint32_t(N * 2)) : "memory");
+      ticket = wq.take();
     }
 
     // ---- pass 0: radix-32 on both columns; scatter (Stockham: butterfly j = 2 lane + c -> 32 j + q) ------------
