@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(kClThreads, 1) spectrum_sense_cluster_kernel(c
   // phase 2 (whose register need is small), so their HBM latency hides behind phase 2 and the epilogue; fp32 IQ keeps
   // only half of them in registers that long (K > 1: none, 64 accumulators), the rest loads in place.
   constexpr int kRawWords = KIND == SCN_KIND_FLOAT_COMPLEX ? 4 : KIND == SCN_KIND_BYTE_COMPLEX ? 1 : 2;
-  constexpr int kPre = KIND == SCN_KIND_FLOAT_COMPLEX ? (AVG ? 0 : SCN_CL_PRE_F32) : 32;
+  // (int16 IQ with K > 1 -- 64 accumulators live across the row FFTs -- spilled with all 32 in registers: 16 is +7 %,
+  //  profiles/r02zo_cluster_int_prefetch_depth_ab.txt; for int8 IQ and K = 1 all 32 measured best)
+  constexpr int kPre = KIND == SCN_KIND_FLOAT_COMPLEX ? (AVG ? 0 : SCN_CL_PRE_F32)
+                     : (KIND == SCN_KIND_SHORT_COMPLEX && AVG) ? 16 : 32;
   const uint32_t lhalf = uint32_t(tid) & 1u, n2base = uint32_t(tid) >> 1;
   uint32_t rawv[32][kRawWords];
   auto load_raw = [&](const uint8_t* buf, int u_begin, int u_end) {
