@@ -76,6 +76,7 @@ void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t
     if (doWrite) {
       uint64_t end = sequenceId + m_postTrigger + 1, cur = m_endSequenceId;
       while (cur < end && !m_endSequenceId.compare_exchange_weak(cur, end)) {}
+      m_sampleQueue->LimitWrite(m_endSequenceId);    // the writer thread may go on up to the extended end
     } else if (sequenceId == m_endSequenceId || (m_averaging > 1 && sequenceId > m_endSequenceId)) {
       // K == 1: the reference's strict equality (process.cpp:262).  With K-FFT averaging only the first id of every
       // K-group arrives here (0, K, 2K, ...), so the end of the window may never be hit exactly: the first group
@@ -88,9 +89,9 @@ void ProcessSamples::ProcessWrite(bool doWrite, double centerFrequency, uint64_t
     TimeToString(m_clock ? m_clock() : time(nullptr), tbuf, sizeof(tbuf));
     snprintf(name, sizeof(name), "%s%s-%.0f-%u", m_fileNameBase.c_str(), tbuf, centerFrequency, ++m_fileCounter);
     const uint64_t dec = sequenceId < m_preTrigger ? sequenceId : m_preTrigger;
-    m_sampleQueue->BeginWrite(sequenceId - dec, name);
-    m_writing = true;
     m_endSequenceId = sequenceId + m_postTrigger + 1;
+    m_sampleQueue->BeginWrite(sequenceId - dec, name, m_endSequenceId);   // ... and never past the planned end
+    m_writing = true;
   }
 }
 

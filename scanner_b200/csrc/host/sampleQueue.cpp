@@ -396,7 +396,7 @@ void SampleQueue::SetWriteConverter(Converter convert) {
   m_convert = convert;
 }
 
-void SampleQueue::BeginWrite(uint64_t startSequenceId, std::string fileName) {
+void SampleQueue::BeginWrite(uint64_t startSequenceId, std::string fileName, uint64_t limit) {
   printf("BeginWrite %s: %lu\n", fileName.c_str(), (unsigned long)startSequenceId);   // messageQueue.h:275-282
   std::unique_lock<std::mutex> lock(m_writeMutex);
   m_writeStartSequenceId = startSequenceId;
@@ -404,7 +404,14 @@ void SampleQueue::BeginWrite(uint64_t startSequenceId, std::string fileName) {
   if (!m_doWrite) return;
   FILE* f = fopen(fileName.c_str(), "w");
   if (!f) { perror(fileName.c_str()); exit(1); }
-  m_writeJobs.push_back(WriteJob{startSequenceId, UINT64_MAX, f});
+  m_writeJobs.push_back(WriteJob{startSequenceId, UINT64_MAX, limit, f});
+  m_conditionWrite.notify_all();
+}
+
+void SampleQueue::LimitWrite(uint64_t limit) {
+  std::unique_lock<std::mutex> lock(m_writeMutex);
+  if (m_writeJobs.empty() || m_writeJobs.back().end != UINT64_MAX) return;      // no open window
+  if (limit > m_writeJobs.back().limit) m_writeJobs.back().limit = limit;
   m_conditionWrite.notify_all();
 }
 
@@ -426,15 +433,17 @@ void SampleQueue::WriteThreadWorker() {
     while (true) {
       // next message of the window: the exact id once it has been processed; an id the history no longer holds
       // is skipped; at shutdown whatever is still parked is flushed
+      // while the window is open nothing at or past the caller's limit is written (it may turn out to lie outside)
+      auto bound = [&] { return job.end != UINT64_MAX ? job.end : job.limit; };
       m_conditionWrite.wait(lock, [&] {
         if (seq < m_evictedBelow) seq = m_evictedBelow;
-        return seq >= job.end || m_writeBuffer.count(seq) != 0 || m_writeShutdown;
+        return seq >= job.end || (seq < bound() && m_writeBuffer.count(seq) != 0) || m_writeShutdown;
       });
-      if (seq >= job.end) break;
+      if (seq >= bound()) break;                          // closed and complete (or shut down at the limit)
       auto it = m_writeBuffer.find(seq);
       if (it == m_writeBuffer.end()) {                    // shutting down: jump to the next parked id, if any
         it = m_writeBuffer.lower_bound(seq);
-        if (it == m_writeBuffer.end() || it->first >= job.end) break;
+        if (it == m_writeBuffer.end() || it->first >= bound()) break;
         seq = it->first;
       }
       MessageType* message = it->second;

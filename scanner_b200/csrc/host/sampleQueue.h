@@ -107,7 +107,12 @@ class SampleQueue {
   // one fights the producer's Allocate for the pool mutex 1024 times)
   void MessageProcessed(const std::vector<MessageType*>& messages);
 
-  void BeginWrite(uint64_t startSequenceId, std::string fileName);
+  // `limit`: no message with an id >= limit is written while the window is still open (the caller's CURRENT idea of
+  // where it will end; LimitWrite raises it when a later trigger extends the window, EndWrite fixes the end).  Without
+  // it the writer thread would race the caller: a message past the end that is already in the history when EndWrite
+  // arrives might or might not have been written.  Default: no limit (the reference's interface, messageQueue.h:275).
+  void BeginWrite(uint64_t startSequenceId, std::string fileName, uint64_t limit = UINT64_MAX);
+  void LimitWrite(uint64_t limit);
   void EndWrite(uint64_t sequenceId);
   // raw buffers of this queue's kind -> interleaved float re/im; false == failure (the writer then exits(1))
   typedef std::function<bool(const void* raw, uint32_t nBuffers, float* out)> Converter;
@@ -160,7 +165,7 @@ class SampleQueue {
   uint32_t m_writeCapacity;
   uint64_t m_evictedBelow = 0;                          // every id below this has left the history
   std::unique_ptr<std::thread> m_writeThread;
-  struct WriteJob { uint64_t cursor, end; FILE* file; };  // one per BeginWrite, written in order, each to completion
+  struct WriteJob { uint64_t cursor, end, limit; FILE* file; };  // one per BeginWrite, written in order, each to completion
   void TrimWriteHistory();                               // caller holds m_writeMutex
   std::deque<WriteJob> m_writeJobs;
   bool m_writeShutdown = false;
