@@ -344,6 +344,32 @@ int main(int argc, char** argv) {
     CHECK(rec.size() == size_t(4) * N * 8);                                  // 4, 5, 6, 7
     f = reinterpret_cast<const float*>(rec.data());
     CHECK(f[3] == 4003.0f && f[size_t(3) * 2 * N + 3] == 7003.0f);
+    // the writer is a thread of its own: with a limit it stays below the planned end of an OPEN window however far
+    // the workers are ahead (without one it would have written 6..11 here before EndWrite arrived); LimitWrite extends
+    for (int extend = 0; extend < 2; extend++) {
+      {
+        SampleQueue q(SampleQueue::FloatComplex, 0, N, 400, false, true);  // history = 40 messages
+        q.SetDropFirstSweep(false);
+        for (int b = 0; b < 12; b++) {
+          for (uint32_t i = 0; i < 2 * N; i++) buf[i] = float(b * 1000 + int(i));
+          q.AppendSamples(reinterpret_cast<fftwf_complex*>(buf.data()), 1e6, 0);
+        }
+        q.SetIsDone();
+        for (int b = 0; b < 12; b++) {
+          SampleQueue::MessageType* m = q.GetNextSamples();
+          if (b == 4) q.BeginWrite(2, path, 6);                              // trigger at 4, pre 2, post 1: [2, 6)
+          if (b == 7 && extend) q.LimitWrite(9);                             // a later trigger: [2, 9)
+          q.MessageProcessed(m);
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));          // the writer has had every chance
+        q.EndWrite(extend ? 9 : 6);
+      }
+      rec = ReadAll(path);
+      const int want = extend ? 7 : 4;
+      CHECK(rec.size() == size_t(want) * N * 8);
+      f = reinterpret_cast<const float*>(rec.data());
+      CHECK(f[5] == 2005.0f && f[size_t(want - 1) * 2 * N + 5] == float((2 + want - 1) * 1000 + 5));
+    }
     // integer kinds without a converter must not write garbage: covered by the GPU tests (SetWriteConverter)
     remove(path);
   }
